@@ -1,0 +1,154 @@
+"""ORACLE tooling (container-only): freeze golden vectors into tests/golden/.
+
+Run in the authoring container, where ``/root/reference`` exists:
+
+    python -m oracle.make_golden
+
+What it writes (all small, all committed):
+
+* ``octree_fixtures.npz``  -- the reference's own known-answer vectors for the
+  integer octree path, re-packed from
+  ``/root/reference/libs/dwconv/test/data/octree/test_00{1..5}.npz`` and
+  ``.../batch_45.npz`` (inputs: points; answers: key, child, nnum, nnum_nempty,
+  merged 27-neighbour table).  Data only, no reference source.
+* ``state_shapes_<cfg>.json`` -- parameter names/shapes of the reference model
+  built by the reference's own ``model_factory`` (the state_dict layout the
+  drop-in must keep loadable).
+* ``descriptors.npz`` -- descriptors computed by the reference's own,
+  unmodified ``models/*.py`` (run on CPU over ``oracle/ocnn_standin.py``) for
+  seeded synthetic submaps and name-seeded weights
+  (``oracle.model_ref.synthetic_state_dict``); and, next to each, the value of
+  ``oracle.model_ref.forward`` at generation time (must agree to 1e-5).
+* ``octree_t.npz`` -- window / relay-token bookkeeping produced by the
+  reference's ``models/octree.py:OctreeT.build_t`` for a CS-Wild-Places batch
+  in which some submaps own zero relay tokens.
+* ``cylindrical.npz`` -- reference ``CylindricalCoordinates`` outputs.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import model_ref as M
+from . import ocnn_standin as S
+from . import octree_ref as R
+
+REF = S.REFERENCE_ROOT
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+# name -> (model cfg, octree depth, [(n_points, aerial)], cloud seed, weight mode)
+CASES = {
+    'oxford_b1_init':   ('oxford', 9, [(4096, False)], 1, 'init'),
+    'oxford_b1_stress': ('oxford', 9, [(4096, False)], 1, 'stress'),
+    'oxford_b4_init':   ('oxford', 9, [(4096, False)] * 4, 2, 'init'),
+    'oxford_b4_stress': ('oxford', 9, [(4096, False)] * 4, 2, 'stress'),
+    'cswp_b4_init':     ('cs-wild-places', 7, [(30000, False), (60000, True)] * 2, 3, 'init'),
+    'cswp_b6_stress':   ('cs-wild-places', 7, [(30000, False)] * 6, 4, 'stress'),
+    'wp_b3_init':       ('wild-places', 7, [(30000, False)] * 3, 5, 'init'),
+    'wp_b3_stress':     ('wild-places', 7, [(8000, False), (30000, False), (500, False)], 6, 'stress'),
+}
+
+
+def case_clouds(name):
+    cfg, depth, spec, seed, mode = CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    clouds = [M.lidar_cloud(n, g, aerial=a) for n, a in spec]
+    if cfg == 'wild-places':
+        clouds = [cylindrical_ref(c) for c in clouds]
+    return clouds
+
+
+def cylindrical_ref(cloud: np.ndarray) -> np.ndarray:
+    """eval/pnv_evaluate.py:166-171 using the reference's own converter."""
+    S.install()
+    from datasets.coordinate_utils import CylindricalCoordinates
+    data = torch.from_numpy(cloud)
+    data = data[torch.linalg.norm(data[:, :2], dim=1) <= 1.0]
+    return CylindricalCoordinates(use_octree=True)(data.clone()).numpy()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    S.install()
+    # ---- 1. integer octree fixtures -----------------------------------------
+    base = f'{REF}/libs/dwconv/test/data/'
+    pack = {}
+    for i in range(1, 6):
+        d = np.load(base + 'octree/test_%03d.npz' % i)
+        for k in ('points', 'key', 'child', 'nnum', 'nnum_nempty'):
+            pack[f't{i}_{k}'] = d[k]
+        pack[f't{i}_depth'] = d['depth']
+        pack[f't{i}_full_depth'] = d['full_depth']
+    b = np.load(base + 'batch_45.npz')
+    for k in ('key', 'child', 'nnum', 'nnum_nempty', 'neigh', 'depth', 'full_depth'):
+        pack[f'b45_{k}'] = b[k]
+    np.savez_compressed(os.path.join(OUT, 'octree_fixtures.npz'), **pack)
+
+    # ---- 2. state_dict layouts ------------------------------------------------
+    models = {}
+    for cfg in ('oxford', 'cs-wild-places', 'wild-places', 'cs-campus3d'):
+        m = S.reference_model(f'{REF}/models/hotformerloc_{cfg}_cfg.txt')
+        models[cfg] = m
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+        with open(os.path.join(OUT, f'state_shapes_{cfg}.json'), 'w') as f:
+            json.dump(shapes, f, indent=0)
+
+    # ---- 3. descriptors from the reference's own model code ---------------------
+    desc = {}
+    for name, (cfg, depth, spec, seed, mode) in CASES.items():
+        m = models[cfg]
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        sd = M.synthetic_state_dict(shapes, mode=mode)
+        m.load_state_dict(sd)
+        clouds = case_clouds(name)
+        with torch.inference_mode():
+            y = m(S.make_batch(clouds, depth))['global'].numpy()
+        hp = M.HParams.from_cfg(f'{REF}/models/hotformerloc_{cfg}_cfg.txt')
+        o = R.build_batch(clouds, depth)
+        g = M.forward(sd, o, hp).numpy()
+        err = np.abs(y - g).max()
+        print(f'{name}: reference-vs-oracle max-abs {err:.2e}', flush=True)
+        assert err < 1e-5, name
+        desc[name + '_reference'] = y
+        desc[name + '_oracle'] = g
+        desc[name + '_nnum_nempty'] = o.nnum_nempty
+    np.savez_compressed(os.path.join(OUT, 'descriptors.npz'), **desc)
+
+    # ---- 4. OctreeT bookkeeping (zero-RT submaps) -------------------------------
+    from models.octree import OctreeT
+    tpack = {}
+    for name in ('cswp_b6_stress', 'oxford_b4_init'):
+        cfg, depth, spec, seed, mode = CASES[name]
+        hp = M.HParams.from_cfg(f'{REF}/models/hotformerloc_{cfg}_cfg.txt')
+        octree = S.make_batch(case_clouds(name), depth)['octree']
+        d0 = depth - hp.stem_down
+        t = OctreeT(octree, hp.patch_size, hp.dilation, True, max_depth=d0,
+                    start_depth=d0 - 3, rt_size=1, ADaPE_mode=hp.ADaPE_mode,
+                    num_pyramid_levels=3, num_octf_levels=1)
+        t.build_t()
+        for d in range(d0 - 3, d0 + 1):
+            tpack[f'{name}_nnum_a_{d}'] = np.array(int(t.nnum_a[d]))
+            tpack[f'{name}_batch_idx_{d}'] = t.batch_idx[d].numpy().astype(np.int16)
+            if d < d0:
+                tpack[f'{name}_num_windows_{d}'] = t.batch_num_windows[d].numpy()
+                tpack[f'{name}_rt_batch_idx_{d}'] = t.rt_batch_idx[d].numpy().astype(np.int16)
+                tpack[f'{name}_rt_init_mask_{d}'] = np.packbits(t.rt_init_mask[d].numpy())
+                tpack[f'{name}_window_stats_{d}'] = t.window_stats[d].numpy()
+        tpack[f'{name}_rt_combined'] = t.batch_num_relay_tokens_combined.numpy()
+        tpack[f'{name}_rt_attn_allowed'] = np.packbits((t.rt_attn_mask == 0).numpy())
+        tpack[f'{name}_rt_attn_shape'] = np.array(t.rt_attn_mask.shape)
+    np.savez_compressed(os.path.join(OUT, 'octree_t.npz'), **tpack)
+
+    # ---- 5. cylindrical conversion ----------------------------------------------
+    g = torch.Generator().manual_seed(7)
+    c = M.lidar_cloud(5000, g)
+    np.savez_compressed(os.path.join(OUT, 'cylindrical.npz'), cloud=c, out=cylindrical_ref(c))
+    print('golden vectors written to', OUT)
+
+
+if __name__ == '__main__':
+    main()

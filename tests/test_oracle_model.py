@@ -1,0 +1,43 @@
+"""Pins oracle/model_ref.py against descriptors produced by the reference's
+own, unmodified models/*.py (tests/golden/descriptors.npz, made by
+oracle/make_golden.py in the authoring container).  fp32, max-abs 1e-5."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as M
+from oracle import octree_ref as R
+from oracle.make_golden import CASES
+
+CFG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                   'hotformerloc_b200', 'models')
+
+
+def _clouds(name):
+    cfg, depth, spec, seed, mode = CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    clouds = [M.lidar_cloud(n, g, aerial=a) for n, a in spec]
+    if cfg == 'wild-places':
+        from hotformerloc_b200.datasets.coordinate_utils import cylindrical_for_octree
+        clouds = [cylindrical_for_octree(c) for c in clouds]
+    return clouds
+
+
+@pytest.mark.parametrize('name', ['oxford_b1_init', 'oxford_b1_stress', 'cswp_b6_stress',
+                                  'wp_b3_stress'])
+def test_oracle_reproduces_reference_descriptors(golden_dir, name):
+    cfg, depth, spec, seed, mode = CASES[name]
+    gold = np.load(os.path.join(golden_dir, 'descriptors.npz'))
+    shapes = json.load(open(os.path.join(golden_dir, f'state_shapes_{cfg}.json')))
+    sd = M.synthetic_state_dict(shapes, mode=mode)
+    hp = M.HParams.from_cfg(os.path.join(CFG, f'hotformerloc_{cfg}_cfg.txt'))
+    o = R.build_batch(_clouds(name), depth)
+    assert np.array_equal(o.nnum_nempty, gold[name + '_nnum_nempty'])
+    g = M.forward(sd, o, hp).numpy()
+    ref = gold[name + '_reference']
+    assert np.abs(g - ref).max() < 1e-5
+    cos = (g * ref).sum(1) / np.linalg.norm(g, axis=1) / np.linalg.norm(ref, axis=1)
+    assert cos.min() > 0.99999
