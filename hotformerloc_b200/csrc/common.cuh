@@ -1,0 +1,54 @@
+// Shared helpers for libhfl_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/hfl.h"
+
+namespace hfl {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define HFL_CHECK_ARG(cond, msg)                                              \
+  do {                                                                        \
+    if (!(cond)) return ::hfl::fail(HFL_ERR_INVALID, "%s (%lld)", msg, (long long)__LINE__); \
+  } while (0)
+
+#define HFL_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess)                                                   \
+      return ::hfl::fail(HFL_ERR_CUDA, "CUDA error: %s (line %lld)",          \
+                         cudaGetErrorString(e__), (long long)__LINE__);       \
+  } while (0)
+
+// kernel<<<...>>> launch + bookkeeping + error peek (no sync)
+#define HFL_LAUNCH(...)                                                       \
+  do {                                                                        \
+    __VA_ARGS__;                                                              \
+    ::hfl::g_launches.fetch_add(1, std::memory_order_relaxed);                \
+    HFL_CUDA(cudaPeekAtLastError());                                          \
+  } while (0)
+
+constexpr int kSMs = 148;
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+inline int grid_for(int64_t n, int threads, int max_blocks = kSMs * 32) {
+  int64_t g = ceil_div(n, threads);
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace hfl

@@ -1,0 +1,566 @@
+// Warp-per-row gather / reduce kernels of the hot path (HBM- / L2-bound; SURVEY.md
+// section 8 rows a5, a8 (first conv), a9, a12, a15):
+//   k_stem_conv    : InputFeature('P') + OctreeConv 3^3 (3 -> 32) + LayerNorm + ReLU
+//   k_cpe_ln       : x += LN(dwconv27(x)) [libs/dwconv/csrc/dwconv.cu:25-42 + CPE norm]
+//                    fused with the block's pre-attention LayerNorm (bf16 GEMM operand)
+//   k_ln_rows      : LayerNorm of gathered rows -> bf16 (relay-token / mixer operand)
+//   k_rt_init      : relay-token init (masked window mean) + ADaPE window statistics
+//                    + ADaPE fc1 (9 -> C, GELU)
+//   k_pool_*       : attention pooling: column softmax statistics + weighted token sum
+//   k_mixer_tail   : Mixer channel_proj / row_proj + L2 normalisation
+// The residual stream is fp32 (x) with a bf16 shadow (xb) that feeds gathers and GEMMs.
+// "hat" layout (hierarchical attention): K window tokens preceded by their relay token,
+//   row(token t) = t + t / K + 1,  row(RT of window w) = w * (K + 1).
+#include "common.cuh"
+
+namespace hfl {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float gelu(float v) {
+  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+}
+__device__ __forceinline__ int64_t hat_row(int64_t t, int K) { return K ? t + t / K + 1 : t; }
+
+template <int V>
+__device__ __forceinline__ void load_bf16(const __nv_bfloat16* p, float (&v)[V]) {
+  if constexpr (V == 8) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  } else {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_bf16(__nv_bfloat16* p, const float (&v)[V]) {
+  uint32_t w[V / 2];
+#pragma unroll
+  for (int j = 0; j < V / 2; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  if constexpr (V == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+}
+template <int V>
+__device__ __forceinline__ void load_f32(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int j = 0; j < V / 4; ++j) {
+    float4 f = reinterpret_cast<const float4*>(p)[j];
+    v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_f32(float* p, const float (&v)[V]) {
+#pragma unroll
+  for (int j = 0; j < V / 4; ++j)
+    reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// LayerNorm of a C = 32*V vector distributed over a warp (lane owns V contiguous channels)
+template <int V>
+__device__ __forceinline__ void warp_ln(float (&v)[V], const float* g, const float* b, int c0,
+                                        float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) s += v[j];
+  const float mean = warp_sum(s) / (32.f * V);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) { float d = v[j] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (32.f * V) + eps);
+  float gg[V], bb[V];
+  load_f32<V>(g + c0, gg);
+  load_f32<V>(b + c0, bb);
+#pragma unroll
+  for (int j = 0; j < V; ++j) v[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
+}
+
+// ---------------------------------------------------------------------------
+// stem: first OctreeConv (Cin = 3) on CUDA cores, one warp per leaf, lane = out channel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stem_conv(const float* __restrict__ leaf_pts, const int32_t* __restrict__ ne, int64_t n,
+            float pscale, const float* __restrict__ w /*[81][32]*/, const float* __restrict__ g,
+            const float* __restrict__ b, __nv_bfloat16* __restrict__ out) {
+  __shared__ float sw[81 * 32];
+  for (int i = threadIdx.x; i < 81 * 32; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const int32_t my = lane < 27 ? __ldg(ne + i * 27 + lane) : -1;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (my >= 0) {
+      fx = leaf_pts[3 * (int64_t)my] * pscale - 1.0f;
+      fy = leaf_pts[3 * (int64_t)my + 1] * pscale - 1.0f;
+      fz = leaf_pts[3 * (int64_t)my + 2] * pscale - 1.0f;
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float x = __shfl_sync(0xffffffffu, fx, k);
+      const float y = __shfl_sync(0xffffffffu, fy, k);
+      const float z = __shfl_sync(0xffffffffu, fz, k);
+      acc += x * sw[(3 * k) * 32 + lane] + y * sw[(3 * k + 1) * 32 + lane] + z * sw[(3 * k + 2) * 32 + lane];
+    }
+    const float mean = warp_sum(acc) * (1.f / 32.f);
+    const float d = acc - mean;
+    const float rstd = rsqrtf(warp_sum(d * d) * (1.f / 32.f) + 1e-5f);
+    const float y = fmaxf(d * rstd * g[lane] + b[lane], 0.f);
+    out[i * 32 + lane] = __float2bfloat16(y);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CPE + LayerNorm fusion.  One warp per row of the (hat or plain) layout.
+// ---------------------------------------------------------------------------
+struct CpeParams {
+  float* x;                    // [rows, C] fp32 residual stream (updated in place)
+  const __nv_bfloat16* xb;     // [rows, C] bf16 shadow (gather source, not modified)
+  const int32_t* ne;           // [n, 27] neighbour table, token index space
+  const float* w;              // [27, C] depth-wise weights
+  const float *g_cpe, *b_cpe;  // CPE LayerNorm
+  const float *g1, *b1;        // block norm1 (NULL: skip)
+  __nv_bfloat16* y1;           // [rows, C] LN1(x) bf16 (NULL: skip)
+  float* cpe_out;              // [n, C] when non-NULL: write LN(dwconv(x)) only, token-compact
+  int64_t n, rows;             // real tokens, layout rows
+  int K;                       // 0 = plain layout, else hat layout window size
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
+  const int lane = threadIdx.x & 31;
+  const int C = 32 * V, c0 = lane * V;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < p.rows; r += nwarps) {
+    int64_t t = r;
+    bool is_rt = false;
+    if (p.K) {
+      const int64_t w = r / (p.K + 1);
+      const int s = (int)(r - w * (p.K + 1));
+      is_rt = s == 0;
+      t = w * p.K + s - 1;
+    }
+    float xv[V];
+    if (!is_rt && t < p.n) {
+      const int32_t my = lane < 27 ? __ldg(p.ne + t * 27 + lane) : -1;
+      float acc[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < 27; ++k) {
+        const int32_t ni = __shfl_sync(0xffffffffu, my, k);
+        if (ni >= 0) {
+          float nv[V], wv[V];
+          load_bf16<V>(p.xb + hat_row(ni, p.K) * C + c0, nv);
+          load_f32<V>(p.w + k * C + c0, wv);
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += wv[j] * nv[j];
+        }
+      }
+      warp_ln<V>(acc, p.g_cpe, p.b_cpe, c0, 1e-5f);
+      if (p.cpe_out) {
+        store_f32<V>(p.cpe_out + t * C + c0, acc);
+        continue;
+      }
+      load_f32<V>(p.x + r * C + c0, xv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) xv[j] += acc[j];
+      store_f32<V>(p.x + r * C + c0, xv);
+    } else {
+      if (p.cpe_out) continue;
+      load_f32<V>(p.x + r * C + c0, xv);     // relay token or padding row: no CPE
+    }
+    if (p.y1) {
+      warp_ln<V>(xv, p.g1, p.b1, c0, 1e-5f);
+      store_bf16<V>(p.y1 + r * C + c0, xv);
+    }
+  }
+}
+
+// LayerNorm of gathered fp32 rows -> compact bf16 rows
+template <int V>
+__global__ void __launch_bounds__(256)
+k_ln_rows(const float* __restrict__ x, const int32_t* __restrict__ rows, int64_t m,
+          const float* __restrict__ g, const float* __restrict__ b, __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int C = 32 * V, c0 = lane * V;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp0; i < m; i += nwarps) {
+    const int64_t r = rows ? (int64_t)__ldg(rows + i) : i;
+    float v[V];
+    load_f32<V>(x + r * C + c0, v);
+    warp_ln<V>(v, g, b, c0, 1e-5f);
+    store_bf16<V>(y + i * C + c0, v);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// relay-token initialisation + ADaPE statistics / fc1, one warp per window
+// ---------------------------------------------------------------------------
+struct RtInitParams {
+  float* x;                  // hat layout [n_win*(K+1), C]; RT rows written
+  const float* src;          // NULL: average x's own token rows; else token-compact [n, C]
+  const short4* xyzb;        // [n_win*K] token table
+  int64_t n, n_win;
+  int K, depth, mode;        // mode: 0 none, 3 pos, 6 var, 9 cov
+  const float *w1, *b1;      // ADaPE fc1 [C, mode], [C]
+  __nv_bfloat16* h;          // [n_win, C] GELU(fc1(stats)) bf16 (fc2 runs on the tensor cores)
+  float* stats_out;          // [n_win, 9] optional (tests)
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) k_rt_init(const RtInitParams p) {
+  const int lane = threadIdx.x & 31;
+  const int C = 32 * V, c0 = lane * V;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float cs = ldexpf(1.0f, 1 - p.depth);
+  for (int64_t w = warp0; w < p.n_win; w += nwarps) {
+    const int64_t t0 = w * p.K;
+    const short id0 = p.xyzb[t0].w;
+    // ---- masked mean of the window's token features ----
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    int cnt = 0;
+    for (int s = 0; s < p.K; ++s) {
+      if (p.xyzb[t0 + s].w != id0) continue;                 // warp-uniform
+      ++cnt;
+      float v[V];
+      if (p.src) {
+        if (t0 + s < p.n) load_f32<V>(p.src + (t0 + s) * C + c0, v);
+        else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[j] = 0.f;
+        }
+      } else {
+        load_f32<V>(p.x + (w * (p.K + 1) + 1 + s) * C + c0, v);
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += v[j];
+    }
+    const float inv = 1.0f / (float)cnt;
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] *= inv;
+    store_f32<V>(p.x + w * (p.K + 1) * C + c0, acc);
+    if (p.mode == 0) continue;
+    // ---- window statistics of the node centres (models/octree.py:285-344) ----
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int s = lane; s < p.K; s += 32) {
+      const short4 q = p.xyzb[t0 + s];
+      if (q.w != id0) continue;
+      const bool real = t0 + s < p.n;
+      sx += real ? q.x * cs - 1.0f : 0.f;
+      sy += real ? q.y * cs - 1.0f : 0.f;
+      sz += real ? q.z * cs - 1.0f : 0.f;
+    }
+    const float fc = fmaxf((float)cnt, 1.0f);
+    const float mx = warp_sum(sx) / fc, my = warp_sum(sy) / fc, mz = warp_sum(sz) / fc;
+    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = lane; s < p.K; s += 32) {
+      const short4 q = p.xyzb[t0 + s];
+      if (q.w != id0) continue;
+      const bool real = t0 + s < p.n;
+      const float dx = (real ? q.x * cs - 1.0f : 0.f) - mx;
+      const float dy = (real ? q.y * cs - 1.0f : 0.f) - my;
+      const float dz = (real ? q.z * cs - 1.0f : 0.f) - mz;
+      cv[0] += dx * dx; cv[1] += dx * dy; cv[2] += dx * dz;
+      cv[3] += dy * dy; cv[4] += dy * dz; cv[5] += dz * dz;
+    }
+    const float den = fmaxf((float)cnt - 1.0f, 1.0f);
+    const float okf = cnt >= 2 ? 1.0f : 0.0f;
+    float st[9];
+    st[0] = mx; st[1] = my; st[2] = mz;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) st[3 + j] = warp_sum(cv[j]) / den * okf;
+    if (p.mode == 6) { st[4] = st[6]; st[5] = st[8]; }      // 'var': diagonal only
+    if (p.stats_out && lane < 9) {
+      float v = st[0];
+#pragma unroll
+      for (int j = 1; j < 9; ++j) v = lane == j ? st[j] : v;
+      p.stats_out[w * 9 + lane] = v;
+    }
+    float hv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float a = p.b1[c0 + j];
+      for (int i = 0; i < p.mode; ++i) a += p.w1[(c0 + j) * p.mode + i] * st[i];
+      hv[j] = gelu(a);
+    }
+    store_bf16<V>(p.h + w * C + c0, hv);
+  }
+}
+
+__global__ void k_hat_rows(int32_t* __restrict__ out, int64_t n, int K, int32_t offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)hat_row(i, K) + offset;
+}
+__global__ void k_remap_hat(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
+                            int K) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = in[i];
+    out[i] = v < 0 ? -1 : (int32_t)hat_row(v, K);
+  }
+}
+__global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                              int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+// ---------------------------------------------------------------------------
+// attention pooling (models/layers/salsa.py:25-55 restricted to each submap's tokens)
+//   logits [rows, ldl] fp32 come from the tcgen05 GEMM x . query^T (hat rows)
+//   pass 1: per (submap, query) max and sum of exp over the submap's tokens
+//   pass 2: out[b, q, :] = sum_t softmax_t * x[t, :]
+// ---------------------------------------------------------------------------
+struct PoolParams {
+  const float* logits;   // [rows, ldl]
+  const float* x;        // [rows, C] fp32 features, hat layout
+  const int32_t* tok_off; // [B+1] token offsets of the submaps at this level
+  float* stat;           // [B, kq, 2] (max, 1/sum) in log2 domain
+  float* out;            // [B, ktot, C]; this level's queries start at q_off
+  int B, kq, ldl, K, C, ktot, q_off;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) k_pool_stats(const PoolParams p) {
+  // grid: (B, ceil(kq/8)); warp = one query column, lanes stride over tokens
+  const int b = blockIdx.x, q = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= p.kq) return;
+  const int64_t t0 = p.tok_off[b], t1 = p.tok_off[b + 1];
+  const float sc = p.scale * 1.4426950408889634f;
+  float m = -INFINITY;
+  for (int64_t t = t0 + lane; t < t1; t += 32)
+    m = fmaxf(m, p.logits[hat_row(t, p.K) * p.ldl + q] * sc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int64_t t = t0 + lane; t < t1; t += 32)
+    s += exp2f(p.logits[hat_row(t, p.K) * p.ldl + q] * sc - m);
+  s = warp_sum(s);
+  if (lane == 0) {
+    p.stat[((size_t)b * p.kq + q) * 2] = m;
+    p.stat[((size_t)b * p.kq + q) * 2 + 1] = s > 0.f ? 1.0f / s : 0.f;
+  }
+}
+
+constexpr int PQ = 16;   // queries per CTA
+__global__ void __launch_bounds__(256) k_pool_sum(const PoolParams p) {
+  // grid: (B, ceil(kq/PQ)); thread = channel (C == blockDim.x)
+  __shared__ float sp[64][PQ];
+  __shared__ float sm[PQ], si[PQ];
+  const int b = blockIdx.x, q0 = blockIdx.y * PQ, c = threadIdx.x;
+  const int nq = min(PQ, p.kq - q0);
+  const int64_t t0 = p.tok_off[b], t1 = p.tok_off[b + 1];
+  const float sc = p.scale * 1.4426950408889634f;
+  if (threadIdx.x < PQ) {
+    const bool ok = (int)threadIdx.x < nq;
+    sm[threadIdx.x] = ok ? p.stat[((size_t)b * p.kq + q0 + threadIdx.x) * 2] : 0.f;
+    si[threadIdx.x] = ok ? p.stat[((size_t)b * p.kq + q0 + threadIdx.x) * 2 + 1] : 0.f;
+  }
+  float acc[PQ];
+#pragma unroll
+  for (int j = 0; j < PQ; ++j) acc[j] = 0.f;
+  for (int64_t tb = t0; tb < t1; tb += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * PQ; i += blockDim.x) {
+      const int tt = i / PQ, j = i % PQ;
+      float pv = 0.f;
+      if (tb + tt < t1 && j < nq)
+        pv = exp2f(p.logits[hat_row(tb + tt, p.K) * p.ldl + q0 + j] * sc - sm[j]) * si[j];
+      sp[tt][j] = pv;
+    }
+    __syncthreads();
+    const int lim = (int)min((int64_t)64, t1 - tb);
+    for (int tt = 0; tt < lim; ++tt) {
+      const float xv = p.x[hat_row(tb + tt, p.K) * p.C + c];
+#pragma unroll
+      for (int j = 0; j < PQ; ++j) acc[j] += sp[tt][j] * xv;
+    }
+  }
+  for (int j = 0; j < nq; ++j)
+    p.out[((size_t)b * p.ktot + p.q_off + q0 + j) * p.C + c] = acc[j];
+}
+
+// Mixer tail (salsa.py:103-111) + F.normalize (hotformerloc.py:55-56); one CTA per submap
+struct TailParams {
+  const float* x;          // [B, kin, C]
+  const float *wc, *bc;    // channel_proj [kout, kin], [kout]
+  const float *wr, *br;    // row_proj [od, C], [od]
+  float* out;              // [B, kout*od]
+  int kin, kout, C, od, normalize;
+};
+__global__ void __launch_bounds__(256) k_mixer_tail(const TailParams p) {
+  extern __shared__ float sh[];
+  float* sy = sh;                       // [kout][C]
+  float* sd = sh + p.kout * p.C;        // [kout*od]
+  __shared__ float red[8];
+  const int b = blockIdx.x, c = threadIdx.x;     // C == blockDim.x
+  const float* xb = p.x + (size_t)b * p.kin * p.C;
+  for (int o = 0; o < p.kout; ++o) {
+    float a = p.bc[o];
+    for (int t = 0; t < p.kin; ++t) a += p.wc[o * p.kin + t] * xb[t * p.C + c];
+    sy[o * p.C + c] = a;
+  }
+  __syncthreads();
+  const int nout = p.kout * p.od;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = warp; e < nout; e += (blockDim.x >> 5)) {
+    const int o = e / p.od, d = e % p.od;
+    float a = 0.f;
+    for (int cc = lane; cc < p.C; cc += 32) a += p.wr[d * p.C + cc] * sy[o * p.C + cc];
+    a = warp_sum(a);
+    if (lane == 0) sd[e] = a + p.br[d];
+  }
+  __syncthreads();
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < nout; e += blockDim.x) ss += sd[e] * sd[e];
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float inv = p.normalize ? 1.0f / fmaxf(sqrtf(tot), 1e-12f) : 1.0f;
+  for (int e = threadIdx.x; e < nout; e += blockDim.x) p.out[(size_t)b * nout + e] = sd[e] * inv;
+}
+
+// PyramidOctGeM (pooling.py:87-103): per-submap generalised mean over a level's tokens
+__global__ void __launch_bounds__(256)
+k_gem_pool(const float* __restrict__ x, const int32_t* __restrict__ tok_off, int K, int C,
+           float pw, float eps, float* __restrict__ out, int ld_out, int col_off) {
+  // grid: (B); thread = channel (strided)
+  const int b = blockIdx.x;
+  const int64_t t0 = tok_off[b], t1 = tok_off[b + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int64_t t = t0; t < t1; ++t) a += powf(fmaxf(x[hat_row(t, K) * C + c], eps), pw);
+    const float cnt = fmaxf((float)(t1 - t0), 1.0f);
+    out[(size_t)b * ld_out + col_off + c] = powf(a / cnt, 1.0f / pw);
+  }
+}
+
+}  // namespace hfl
+
+using namespace hfl;
+
+#define ROWS_GRID(n) grid_for((int64_t)(n) * 32, 256, kSMs * 16)
+
+extern "C" {
+
+int hfl_stem_conv(const float* leaf_pts, const int32_t* ne, int64_t n, int32_t depth,
+                  const float* w, const float* g, const float* b, void* out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n == 0) return HFL_OK;
+  HFL_CHECK_ARG(leaf_pts && ne && w && g && b && out, "null argument");
+  HFL_LAUNCH((k_stem_conv<<<ROWS_GRID(n), 256, 0, st>>>(leaf_pts, ne, n, ldexpf(1.0f, 1 - depth), w, g, b, (__nv_bfloat16*)out)));
+  return HFL_OK;
+}
+
+int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const float* w, const float* g_cpe,
+               const float* b_cpe, const float* g1, const float* b1, void* y1, float* cpe_out,
+               int64_t n, int64_t rows, int32_t C, int32_t K, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (rows == 0) return HFL_OK;
+  HFL_CHECK_ARG(x && xb && ne && w && g_cpe && b_cpe, "null argument");
+  HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
+  HFL_CHECK_ARG(!y1 || (g1 && b1), "norm1 parameters missing");
+  CpeParams p{x, (const __nv_bfloat16*)xb, ne, w, g_cpe, b_cpe, g1, b1, (__nv_bfloat16*)y1, cpe_out, n, rows, K};
+  if (C == 128) HFL_LAUNCH((k_cpe_ln<4><<<ROWS_GRID(rows), 256, 0, st>>>(p)));
+  else HFL_LAUNCH((k_cpe_ln<8><<<ROWS_GRID(rows), 256, 0, st>>>(p)));
+  return HFL_OK;
+}
+
+int hfl_ln_rows(const float* x, const int32_t* rows, int64_t m, int32_t C, const float* g,
+                const float* b, void* y, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (m == 0) return HFL_OK;
+  HFL_CHECK_ARG(x && g && b && y, "null argument");
+  HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
+  if (C == 128) HFL_LAUNCH((k_ln_rows<4><<<ROWS_GRID(m), 256, 0, st>>>(x, rows, m, g, b, (__nv_bfloat16*)y)));
+  else HFL_LAUNCH((k_ln_rows<8><<<ROWS_GRID(m), 256, 0, st>>>(x, rows, m, g, b, (__nv_bfloat16*)y)));
+  return HFL_OK;
+}
+
+int hfl_rt_init(float* x, const float* src, const int16_t* xyzb, int64_t n, int64_t n_win,
+                int32_t K, int32_t C, int32_t depth, int32_t mode, const float* w1,
+                const float* b1, void* h, float* stats_out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_win == 0) return HFL_OK;
+  HFL_CHECK_ARG(x && xyzb, "null argument");
+  HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
+  HFL_CHECK_ARG(mode == 0 || ((mode == 3 || mode == 6 || mode == 9) && w1 && b1 && h), "bad ADaPE mode");
+  RtInitParams p{x, src, (const short4*)xyzb, n, n_win, K, depth, mode, w1, b1, (__nv_bfloat16*)h, stats_out};
+  if (C == 128) HFL_LAUNCH((k_rt_init<4><<<ROWS_GRID(n_win), 256, 0, st>>>(p)));
+  else HFL_LAUNCH((k_rt_init<8><<<ROWS_GRID(n_win), 256, 0, st>>>(p)));
+  return HFL_OK;
+}
+
+int hfl_hat_rows(int32_t* out, int64_t n, int32_t K, int32_t offset, void* stream_) {
+  if (n == 0) return HFL_OK;
+  HFL_LAUNCH((k_hat_rows<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(out, n, K, offset)));
+  return HFL_OK;
+}
+int hfl_remap_hat(const int32_t* in, int32_t* out, int64_t n, int32_t K, void* stream_) {
+  if (n == 0) return HFL_OK;
+  HFL_LAUNCH((k_remap_hat<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(in, out, n, K)));
+  return HFL_OK;
+}
+int hfl_f32_to_bf16(const float* in, void* out, int64_t n, void* stream_) {
+  if (n == 0) return HFL_OK;
+  HFL_LAUNCH((k_f32_to_bf16<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(in, (__nv_bfloat16*)out, n)));
+  return HFL_OK;
+}
+
+int hfl_attn_pool(const float* logits, const float* x, const int32_t* tok_off, float* stat,
+                  float* out, int32_t B, int32_t kq, int32_t ldl, int32_t K, int32_t C,
+                  int32_t ktot, int32_t q_off, float scale, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HFL_CHECK_ARG(logits && x && tok_off && stat && out, "null argument");
+  HFL_CHECK_ARG(C == 256 || C == 128, "C must equal the CTA size (128/256)");
+  PoolParams p{logits, x, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale};
+  HFL_LAUNCH((k_pool_stats<<<dim3(B, (kq + 7) / 8), 256, 0, st>>>(p)));
+  HFL_LAUNCH((k_pool_sum<<<dim3(B, (kq + PQ - 1) / PQ), C, 0, st>>>(p)));
+  return HFL_OK;
+}
+
+int hfl_mixer_tail(const float* x, const float* wc, const float* bc, const float* wr,
+                   const float* br, float* out, int32_t B, int32_t kin, int32_t kout, int32_t C,
+                   int32_t od, int32_t normalize, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  HFL_CHECK_ARG(x && wc && bc && wr && br && out, "null argument");
+  HFL_CHECK_ARG(C == 256 || C == 128, "C must equal the CTA size (128/256)");
+  TailParams p{x, wc, bc, wr, br, out, kin, kout, C, od, normalize};
+  const int smem = (kout * C + kout * od) * 4;
+  static int smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    HFL_CUDA(cudaFuncSetAttribute(k_mixer_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  HFL_LAUNCH((k_mixer_tail<<<B, C, smem, st>>>(p)));
+  return HFL_OK;
+}
+
+int hfl_gem_pool(const float* x, const int32_t* tok_off, int32_t B, int32_t K, int32_t C, float pw,
+                 float eps, float* out, int32_t ld_out, int32_t col_off, void* stream_) {
+  HFL_CHECK_ARG(x && tok_off && out, "null argument");
+  HFL_LAUNCH((k_gem_pool<<<B, 256, 0, (cudaStream_t)stream_>>>(x, tok_off, K, C, pw, eps, out, ld_out, col_off)));
+  return HFL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+"""Thin Python wrappers over the C ABI (include/hfl.h).  Tensors in, tensors
+out; no math happens here.  Every function raises HflError on failure."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native as N
+
+_p = N.ptr
+
+
+def _s():
+    return N.stream()
+
+
+def gather_gemm(A: torch.Tensor, W: torch.Tensor, *, idx: Optional[torch.Tensor] = None,
+                M: Optional[int] = None, KD: int = 1, bias=None, res=None, act: int = 0,
+                out_v_f32=None, out_v_bf16=None, ln=None, relu: bool = False,
+                y_mapped: bool = False, out_y_f32=None, out_y_bf16=None, out_rows=None):
+    """See hfl_gather_gemm.  A: [rows, Cin] bf16; W: [N, KD*Cin] bf16; idx: [M, KD] int32."""
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    Cin = A.shape[1]
+    Nn = W.shape[0]
+    assert W.shape[1] == KD * Cin, (W.shape, KD, Cin)
+    if M is None:
+        M = idx.shape[0] if idx is not None else A.shape[0]
+    if idx is not None:
+        assert idx.dtype == torch.int32 and idx.shape[1] == KD
+    g, b = (ln if ln is not None else (None, None))
+    N.check(N.lib().hfl_gather_gemm(
+        _p(A), _p(idx), _p(W), M, Nn, KD, Cin, _p(bias), _p(res), act, _p(out_v_f32),
+        _p(out_v_bf16), _p(g), _p(b), int(relu), int(y_mapped), _p(out_y_f32), _p(out_y_bf16),
+        _p(out_rows), _s()))
+
+
+def window_attn(qkv, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
+    N.check(N.lib().hfl_window_attn(_p(qkv), _p(out), _p(xyzb), _p(rpe), n_win, H, C, K, dil,
+                                    int(hat), bnd, float(scale), _s()))
+
+
+def varlen_attn(qkv, out, cu, ids, B, max_len, H, C, scale):
+    N.check(N.lib().hfl_varlen_attn(_p(qkv), _p(out), _p(cu), _p(ids), B, max_len, H, C,
+                                    float(scale), _s()))
+
+
+def stem_conv(leaf_pts, ne, n, depth, w, g, b, out):
+    N.check(N.lib().hfl_stem_conv(_p(leaf_pts), _p(ne), n, depth, _p(w), _p(g), _p(b), _p(out), _s()))
+
+
+def cpe_ln(x, xb, ne, w, g_cpe, b_cpe, g1, b1, y1, cpe_out, n, rows, C, K):
+    N.check(N.lib().hfl_cpe_ln(_p(x), _p(xb), _p(ne), _p(w), _p(g_cpe), _p(b_cpe), _p(g1), _p(b1),
+                               _p(y1), _p(cpe_out), n, rows, C, K, _s()))
+
+
+def ln_rows(x, rows, m, C, g, b, y):
+    N.check(N.lib().hfl_ln_rows(_p(x), _p(rows), m, C, _p(g), _p(b), _p(y), _s()))
+
+
+def rt_init(x, src, xyzb, n, n_win, K, C, depth, mode, w1, b1, h, stats_out=None):
+    N.check(N.lib().hfl_rt_init(_p(x), _p(src), _p(xyzb), n, n_win, K, C, depth, mode, _p(w1),
+                                _p(b1), _p(h), _p(stats_out), _s()))
+
+
+def hat_rows(out, n, K, offset=0):
+    N.check(N.lib().hfl_hat_rows(_p(out), n, K, offset, _s()))
+
+
+def remap_hat(src, out, n, K):
+    N.check(N.lib().hfl_remap_hat(_p(src), _p(out), n, K, _s()))
+
+
+def f32_to_bf16(src, out):
+    N.check(N.lib().hfl_f32_to_bf16(_p(src), _p(out), src.numel(), _s()))
+
+
+def attn_pool(logits, x, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale):
+    N.check(N.lib().hfl_attn_pool(_p(logits), _p(x), _p(tok_off), _p(stat), _p(out), B, kq, ldl, K,
+                                  C, ktot, q_off, float(scale), _s()))
+
+
+def mixer_tail(x, wc, bc, wr, br, out, B, kin, kout, C, od, normalize):
+    N.check(N.lib().hfl_mixer_tail(_p(x), _p(wc), _p(bc), _p(wr), _p(br), _p(out), B, kin, kout, C,
+                                   od, int(normalize), _s()))
+
+
+def gem_pool(x, tok_off, B, K, C, pw, eps, out, ld_out, col_off):
+    N.check(N.lib().hfl_gem_pool(_p(x), _p(tok_off), B, K, C, float(pw), float(eps), _p(out),
+                                 ld_out, col_off, _s()))
+
+
+def knn_topk(q: torch.Tensor, db: torch.Tensor, k: int = 25, idx_offset: int = 0):
+    """Exact L2 top-k of every query row against a database shard; returns
+    (squared distances [nq,k] fp32, indices [nq,k] int32) sorted by (dist, idx)."""
+    assert q.dtype == torch.float32 and db.dtype == torch.float32
+    nq, dim = q.shape
+    od = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    oi = torch.empty((nq, k), dtype=torch.int32, device=q.device)
+    N.check(N.lib().hfl_knn_topk(_p(q.contiguous()), nq, _p(db.contiguous()), db.shape[0], dim, k,
+                                 idx_offset, _p(od), _p(oi), _s()))
+    return od, oi
+
+
+def topk_merge(parts_d: torch.Tensor, parts_i: torch.Tensor):
+    """[parts, nq, k] partial lists -> global [nq, k]."""
+    P, nq, k = parts_d.shape
+    od = torch.empty((nq, k), dtype=torch.float32, device=parts_d.device)
+    oi = torch.empty((nq, k), dtype=torch.int32, device=parts_d.device)
+    N.check(N.lib().hfl_topk_merge(_p(parts_d.contiguous()), _p(parts_i.contiguous()), P, nq, k,
+                                   _p(od), _p(oi), _s()))
+    return od, oi

@@ -1,0 +1,256 @@
+"""GPU numerics of every kernel behind include/hfl.h against a plain PyTorch fp32
+statement of the same op (on the same bf16-rounded operands).  Tolerances are
+written next to each check."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from hotformerloc_b200 import ops
+    return ops
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+DEV = 'cuda'
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 128), (1000, 256, 256), (4100, 384, 128),
+                                   (777, 768, 256), (3000, 1024, 256), (513, 256, 1024),
+                                   (130, 64, 256), (50000, 256, 256)])
+def test_gemm_dense_bias(M, N, K):
+    torch.manual_seed(0)
+    A = _bf(torch.randn(M, K, device=DEV))
+    W = _bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV)
+    out = torch.empty(M, N, device=DEV)
+    outb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    _ops().gather_gemm(A, W, bias=bias, out_v_f32=out, out_v_bf16=outb)
+    ref = A.float() @ W.float().t() + bias
+    assert torch.allclose(out, ref, atol=2e-3, rtol=1e-3), (out - ref).abs().max()
+    assert torch.allclose(outb.float(), ref, atol=3e-2, rtol=1e-2)
+
+
+def test_gemm_gelu_residual_ln_rowmap():
+    torch.manual_seed(1)
+    M, N, K, R = 5000, 256, 512, 9000
+    A = _bf(torch.randn(M, K, device=DEV))
+    W = _bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    bias = torch.randn(N, device=DEV)
+    g, b = torch.randn(N, device=DEV), torch.randn(N, device=DEV)
+    rows = torch.randperm(R, device=DEV)[:M].to(torch.int32)
+    rows[17] = -1
+    x = torch.randn(R, N, device=DEV)
+    x0 = x.clone()
+    y = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    xb = torch.zeros(R, N, device=DEV, dtype=torch.bfloat16)
+    _ops().gather_gemm(A, W, bias=bias, res=x, out_v_f32=x, out_v_bf16=xb, ln=(g, b),
+                       out_y_bf16=y, out_rows=rows)
+    v = A.float() @ W.float().t() + bias
+    live = rows >= 0
+    ref_x = x0.clone()
+    ref_x[rows[live].long()] = x0[rows[live].long()] + v[live]
+    assert torch.allclose(x, ref_x, atol=2e-3, rtol=1e-3)
+    assert torch.allclose(xb.float()[rows[live].long()], ref_x[rows[live].long()], atol=5e-2, rtol=1e-2)
+    ref_y = F.layer_norm(ref_x[rows.clamp(min=0).long()], (N,), g, b, 1e-5)
+    assert torch.allclose(y.float()[live], ref_y[live], atol=5e-2, rtol=2e-2)
+    # GELU + relu-after-LN variants
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    _ops().gather_gemm(A, W, bias=bias, act=1, out_v_bf16=out)
+    assert torch.allclose(out.float(), F.gelu(v), atol=3e-2, rtol=1e-2)
+    yf = torch.empty(M, N, device=DEV)
+    _ops().gather_gemm(A, W, ln=(g, b), relu=True, out_y_f32=yf)
+    assert torch.allclose(yf, F.relu(F.layer_norm(A.float() @ W.float().t(), (N,), g, b, 1e-5)),
+                          atol=5e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize('KD,Cin,N', [(27, 64, 64), (8, 32, 64), (27, 128, 128), (8, 256, 256),
+                                      (8, 64, 128)])
+def test_gemm_gather_is_octree_conv(KD, Cin, N):
+    torch.manual_seed(2)
+    rows_a, M = 3000, 2500
+    A = _bf(torch.randn(rows_a, Cin, device=DEV))
+    W3 = torch.randn(KD, Cin, N, device=DEV) / math.sqrt(KD * Cin)
+    Wt = _bf(W3.flatten(0, 1).t().contiguous())
+    idx = torch.randint(-1, rows_a, (M, KD), device=DEV, dtype=torch.int32)
+    idx[idx % 3 == 0] = -1
+    out = torch.empty(M, N, device=DEV)
+    _ops().gather_gemm(A, Wt, idx=idx, KD=KD, out_v_f32=out)
+    buf = A.float()[idx.clamp(min=0).long()] * (idx >= 0).unsqueeze(-1)
+    ref = buf.flatten(1) @ Wt.float().t()
+    assert torch.allclose(out, ref, atol=3e-3, rtol=1e-3), (out - ref).abs().max()
+
+
+def _tokens(n_pad, n, B, K):
+    xyz = torch.randint(0, 128, (n_pad, 3), dtype=torch.int16)
+    bid = torch.sort(torch.randint(0, B, (n_pad,))).values.to(torch.int16)
+    bid[n:] = B
+    xyz[n:] = 0
+    return torch.cat([xyz, bid[:, None]], 1).contiguous()
+
+
+def _ref_window_attn(qkv, tok, rpe, K, dil, hat, H, bnd):
+    rows, C3 = qkv.shape
+    C = C3 // 3
+    n_pad = tok.shape[0]
+    t = torch.arange(n_pad)
+    if hat:
+        win_tok = t.view(-1, K)
+        W = win_tok.shape[0]
+        rowidx = (torch.arange(W)[:, None] * (K + 1) + torch.arange(K + 1)[None])
+        ids = torch.cat([tok[win_tok[:, :1], 3], tok[win_tok, 3]], 1).long()
+        xyz = torch.cat([torch.zeros(W, 1, 3, dtype=torch.long), tok[win_tok][..., :3].long()], 1)
+    else:
+        rowidx = t.view(-1, K) if dil == 1 else t.view(-1, K, dil).transpose(1, 2).reshape(-1, K)
+        ids = tok[rowidx, 3].long()
+        xyz = tok[rowidx][..., :3].long()
+    x = qkv.float().cpu()[rowidx]                                        # (W,L,3C)
+    W_, L = rowidx.shape
+    q, k, v = x.view(W_, L, 3, H, 16).permute(2, 0, 3, 1, 4)
+    att = (q @ k.transpose(-1, -2)) * 0.25
+    bias = torch.zeros(W_, 1, L, L)
+    bias.masked_fill_((ids[:, :, None] != ids[:, None, :])[:, None], float('-inf'))
+    if rpe is not None:
+        num = 2 * bnd + 1
+        rel = (xyz[:, :, None] - xyz[:, None, :]).clamp(-bnd, bnd) + bnd
+        r = sum(rpe.cpu()[rel[..., a] + a * num] for a in range(3)).permute(0, 3, 1, 2)
+        if hat:
+            r[:, :, 0, :] = 0
+            r[:, :, :, 0] = 0
+        bias = bias + r
+    o = ((att + bias).softmax(-1) @ v).transpose(1, 2).reshape(W_, L, C)
+    out = torch.zeros(rows, C)
+    out[rowidx.reshape(-1)] = o.reshape(-1, C)
+    return out
+
+
+@pytest.mark.parametrize('K,dil,hat,H', [(48, 1, False, 8), (48, 4, False, 8), (48, 1, True, 16),
+                                         (64, 1, True, 16), (64, 4, False, 8), (32, 1, True, 8)])
+def test_window_attention(K, dil, hat, H):
+    torch.manual_seed(3)
+    C = 16 * H
+    n_pad, n, B = K * 4 * 5, K * 4 * 5 - 37, 3
+    tok = _tokens(n_pad, n, B, K)
+    n_win = n_pad // K
+    rows = n_win * (K + 1) if hat else n_pad
+    qkv = _bf(torch.randn(rows, 3 * C, device=DEV))
+    bnd = int(0.8 * K * dil ** 0.5)
+    rpe = (torch.randn(3 * (2 * bnd + 1), H) * 0.5).to(DEV)
+    out = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
+    _ops().window_attn(qkv, out, tok.to(DEV), rpe, n_win, H, C, K, dil, hat, bnd, 0.25)
+    ref = _ref_window_attn(qkv, tok, rpe, K, dil, hat, H, bnd)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err < 3e-2, err            # bf16 probabilities / outputs
+
+
+def test_varlen_attention():
+    torch.manual_seed(4)
+    H, C = 16, 256
+    lens = [168, 33, 1, 300, 80, 81]
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32)
+    tot = int(cu[-1])
+    ids = torch.cat([torch.full((l,), i, dtype=torch.int32) for i, l in enumerate(lens)])
+    ids[-5:] = len(lens)                     # padding relay tokens of the last submap
+    qkv = _bf(torch.randn(tot, 3 * C, device=DEV))
+    out = torch.zeros(tot, C, device=DEV, dtype=torch.bfloat16)
+    _ops().varlen_attn(qkv, out, cu.to(DEV), ids.to(DEV), len(lens), max(lens), H, C, 0.25)
+    x = qkv.float().cpu()
+    for b, l in enumerate(lens):
+        s = int(cu[b])
+        q, k, v = x[s:s + l].view(l, 3, H, 16).permute(1, 2, 0, 3)
+        att = (q @ k.transpose(-1, -2)) * 0.25
+        i = ids[s:s + l]
+        att.masked_fill_((i[:, None] != i[None, :])[None], float('-inf'))
+        ref = (att.softmax(-1) @ v).transpose(0, 1).reshape(l, C)
+        err = (out[s:s + l].float().cpu() - ref).abs().max().item()
+        assert err < 3e-2, (b, err)
+
+
+@pytest.mark.parametrize('C,K', [(128, 0), (256, 48), (256, 64)])
+def test_cpe_ln(C, K):
+    torch.manual_seed(5)
+    n = 1000
+    n_pad = -(-n // (4 * (K or 48))) * 4 * (K or 48)
+    rows = n_pad // K * (K + 1) if K else n_pad
+    tok_row = (torch.arange(n_pad) + torch.arange(n_pad) // K + 1) if K else torch.arange(n_pad)
+    x = torch.zeros(rows, C)
+    x[tok_row[:n]] = torch.randn(n, C)
+    if K:
+        x[::K + 1] = torch.randn(rows // (K + 1), C)
+    ne = torch.randint(-1, n, (n, 27), dtype=torch.int32)
+    ne[torch.rand(n, 27) < 0.6] = -1
+    w = torch.randn(27, C) / 5
+    g_c, b_c, g1, b1 = (torch.randn(C) for _ in range(4))
+    xd = x.to(DEV)
+    xb = _bf(xd)
+    y1 = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
+    _ops().cpe_ln(xd, xb, ne.to(DEV), w.to(DEV), g_c.to(DEV), b_c.to(DEV), g1.to(DEV), b1.to(DEV),
+                  y1, None, n, rows, C, K)
+    src = xb.float().cpu()[tok_row[:n]]
+    buf = src[ne.clamp(min=0).long()] * (ne >= 0).unsqueeze(-1)
+    dw = torch.einsum('ikc,kc->ic', buf, w)
+    ref = x.clone()
+    ref[tok_row[:n]] += F.layer_norm(dw, (C,), g_c, b_c, 1e-5)
+    assert torch.allclose(xd.cpu(), ref, atol=2e-4, rtol=1e-4), (xd.cpu() - ref).abs().max()
+    ref_y = F.layer_norm(ref, (C,), g1, b1, 1e-5)
+    live = torch.zeros(rows, dtype=torch.bool)
+    live[tok_row[:n]] = True
+    if K:
+        live[::K + 1] = True
+    assert torch.allclose(y1.float().cpu()[live], ref_y[live], atol=6e-2, rtol=2e-2)
+    # cpe-only mode
+    out = torch.zeros(n, C, device=DEV)
+    _ops().cpe_ln(xd, xb, ne.to(DEV), w.to(DEV), g_c.to(DEV), b_c.to(DEV), None, None, None, out,
+                  n, rows, C, K)
+    assert torch.allclose(out.cpu(), F.layer_norm(dw, (C,), g_c, b_c, 1e-5), atol=2e-4, rtol=1e-4)
+
+
+def test_stem_conv_and_ln_rows():
+    torch.manual_seed(6)
+    n, D = 3000, 9
+    pts = torch.rand(n, 3) * 2 ** D
+    ne = torch.randint(-1, n, (n, 27), dtype=torch.int32)
+    ne[torch.rand(n, 27) < 0.5] = -1
+    w = torch.randn(27, 3, 32) / 9
+    g, b = torch.randn(32), torch.randn(32)
+    out = torch.zeros(n, 32, device=DEV, dtype=torch.bfloat16)
+    _ops().stem_conv(pts.to(DEV), ne.to(DEV), n, D, w.flatten(0, 1).contiguous().to(DEV),
+                     g.to(DEV), b.to(DEV), out)
+    f = pts * 2 ** (1 - D) - 1
+    buf = f[ne.clamp(min=0).long()] * (ne >= 0).unsqueeze(-1)
+    ref = F.relu(F.layer_norm(buf.flatten(1) @ w.flatten(0, 1), (32,), g, b, 1e-5))
+    assert torch.allclose(out.float().cpu(), ref, atol=3e-2, rtol=1e-2)
+    x = torch.randn(500, 256)
+    rows = torch.randperm(500)[:200].to(torch.int32)
+    g, b = torch.randn(256), torch.randn(256)
+    y = torch.zeros(200, 256, device=DEV, dtype=torch.bfloat16)
+    _ops().ln_rows(x.to(DEV), rows.to(DEV), 200, 256, g.to(DEV), b.to(DEV), y)
+    assert torch.allclose(y.float().cpu(), F.layer_norm(x[rows.long()], (256,), g, b, 1e-5),
+                          atol=6e-2, rtol=2e-2)
+
+
+def test_knn_matches_bruteforce():
+    torch.manual_seed(7)
+    db = F.normalize(torch.randn(3000, 256), dim=1).to(DEV)
+    q = F.normalize(torch.randn(700, 256), dim=1).to(DEV)
+    d, i = _ops().knn_topk(q, db, 25)
+    ref = torch.cdist(q.double(), db.double()) ** 2
+    rd, ri = ref.topk(25, dim=1, largest=False)
+    assert torch.allclose(d.double(), rd, atol=1e-5)
+    # same neighbours up to fp32 near-ties: every returned index is within 1e-6 of the true k-th
+    true_d = ref.gather(1, i.long())
+    assert bool((true_d <= rd[:, -1:] + 1e-6).all())
+    assert (i.long() == ri).float().mean() > 0.999
+    assert bool((d[:, 1:] >= d[:, :-1]).all())
+    # sharded search + merge == global search
+    parts = [(_ops().knn_topk(q, db[s:s + 1000], 25, idx_offset=s)) for s in (0, 1000, 2000)]
+    md, mi = _ops().topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi, i) and torch.equal(md, d)
