@@ -12,8 +12,7 @@ from oracle import model_ref as M
 from oracle import octree_ref as R
 from oracle.make_golden import CASES
 
-CFG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                   'hotformerloc_b200', 'models')
+from hotformerloc_b200.config.presets import write_configs
 
 
 def _clouds(name):
@@ -28,12 +27,12 @@ def _clouds(name):
 
 @pytest.mark.parametrize('name', ['oxford_b1_init', 'oxford_b1_stress', 'cswp_b6_stress',
                                   'wp_b3_stress'])
-def test_oracle_reproduces_reference_descriptors(golden_dir, name):
+def test_oracle_reproduces_reference_descriptors(golden_dir, name, tmp_path):
     cfg, depth, spec, seed, mode = CASES[name]
     gold = np.load(os.path.join(golden_dir, 'descriptors.npz'))
     shapes = json.load(open(os.path.join(golden_dir, f'state_shapes_{cfg}.json')))
     sd = M.synthetic_state_dict(shapes, mode=mode)
-    hp = M.HParams.from_cfg(os.path.join(CFG, f'hotformerloc_{cfg}_cfg.txt'))
+    hp = M.HParams.from_cfg(write_configs(str(tmp_path), cfg)['model_config'])
     o = R.build_batch(_clouds(name), depth)
     assert np.array_equal(o.nnum_nempty, gold[name + '_nnum_nempty'])
     g = M.forward(sd, o, hp).numpy()
