@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the HOTFormerLoc embedding hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic submaps:
+raw points -> batched octree build -> hierarchical octree transformer -> (B,256)
+descriptors.  Default workload = BASELINE.json configs[1]: Oxford cfg, 256
+synthetic 4096-point submaps, bf16 tensor-core compute with fp32 accumulation,
+random-init weights.  Prints ONE JSON line (see the driver contract).
+
+  value        submaps/s with the packed points already resident in HBM
+  e2e          same metric through the reference-facing API with HOST buffers
+               (pinned H2D of the points inside the timed region, D2H of descriptors)
+  roofline     dominant kernel family (time share measured live with CUDA events)
+  cpu_baseline the oracle (CPU port of the reference path) on a bounded sample
+
+Multi-GPU (torchrun, one rank per GPU): evaluation batches are sharded across
+ranks (batch t -> rank t mod W), no data-path collective
+except the descriptor all-gather; weak scaling; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = 'submaps_per_sec_octree_build_plus_embed'
+UNIT = 'submaps/s'
+
+
+def synthetic_batches(n_batches, B, P, seed0=1000):
+    from oracle.model_ref import lidar_cloud          # generator only (shared with the tests)
+    out = []
+    for i in range(n_batches):
+        g = torch.Generator().manual_seed(seed0 + i)
+        out.append([lidar_cloud(P, g) for _ in range(B)])
+    return out
+
+
+def make_model(cfg_name, device):
+    from hotformerloc_b200.config.presets import write_configs, TRAIN_PRESETS
+    from hotformerloc_b200.misc.utils import ModelParams
+    from hotformerloc_b200.models.model_factory import model_factory
+    d = tempfile.mkdtemp(prefix='hfl_cfg_')
+    paths = write_configs(d, cfg_name, dataset_folder=d)
+    torch.manual_seed(0)
+    model = model_factory(ModelParams(paths['model_config']))
+    return model.to(device).eval(), paths, TRAIN_PRESETS[cfg_name]['octree_depth']
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap'}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def kernel_profile(model, octree_fn):
+    """Per kernel-family device time + algorithmic work for one step, using CUDA
+    events on the launching stream (an instrumented extra step, not the timed one)."""
+    from hotformerloc_b200 import ops, octree as oct_mod
+    rec = []
+
+    def wrap(name, fn, work):
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            rec.append((name, s, e, work(*a, **k)))
+            return r
+        return inner
+
+    def gemm_work(A, W, **k):
+        M = k.get('M') or (k['idx'].shape[0] if k.get('idx') is not None else A.shape[0])
+        return ('flop', 2.0 * M * W.shape[0] * W.shape[1])
+
+    def attn_work(qkv, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
+        L = K + (1 if hat else 0)
+        return ('flop', 4.0 * n_win * L * L * C)
+
+    def cpe_work(x, xb, ne, w, g, b, g1, b1, y1, cpe_out, n, rows, C, K):
+        return ('byte', rows * C * (4 + 4 + 2) + n * (27 * 4 + 2 * C))
+
+    saved = {}
+    patches = {'gather_gemm': gemm_work, 'window_attn': attn_work, 'cpe_ln': cpe_work}
+    for name, work in patches.items():
+        saved[name] = getattr(ops, name)
+        setattr(ops, name, wrap(name, saved[name], work))
+    others = ['varlen_attn', 'stem_conv', 'ln_rows', 'rt_init', 'attn_pool', 'mixer_tail',
+              'hat_rows', 'remap_hat']
+    for name in others:
+        saved[name] = getattr(ops, name)
+        setattr(ops, name, wrap(name, saved[name], lambda *a, **k: ('none', 0.0)))
+    s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        s0.record()
+        o = octree_fn()
+        e0.record()
+        model({'octree': o})
+        torch.cuda.synchronize()
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
+    fam = {'octree_build': {'ms': s0.elapsed_time(e0), 'launches': 0, 'flop': 0.0, 'byte': 0.0}}
+    for name, s, e, (kind, amount) in rec:
+        f = fam.setdefault(name, {'ms': 0.0, 'launches': 0, 'flop': 0.0, 'byte': 0.0})
+        f['ms'] += s.elapsed_time(e)
+        f['launches'] += 1
+        if kind in ('flop', 'byte'):
+            f[kind] += amount
+    return fam
+
+
+def run_native(args, rank, world, device):
+    from hotformerloc_b200 import native
+    from hotformerloc_b200.octree import build_batch, build_batch_device
+    import torch.distributed as dist
+    model, paths, depth = make_model(args.config, device)
+    B, P = args.batch, args.points
+    n_pool = 3
+    batches = synthetic_batches(n_pool, B, P, seed0=1000 + 17 * rank)
+    dev_batches = []
+    for clouds in batches:
+        pts = torch.from_numpy(np.concatenate(clouds)).to(device)
+        off = torch.tensor(np.concatenate([[0], np.cumsum([len(c) for c in clouds])]),
+                           dtype=torch.int32, device=device)
+        dev_batches.append((pts, off))
+
+    def step_resident(i):
+        pts, off = dev_batches[i % n_pool]
+        o = build_batch_device(pts, off, depth, 2)
+        return model({'octree': o})['global']
+
+    def step_e2e(i):
+        o = build_batch(batches[i % n_pool], depth, 2, device)
+        return model({'octree': o})['global'].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(desc):
+        if world > 1:
+            out = torch.empty((world,) + tuple(desc.shape), dtype=desc.dtype, device=desc.device)
+            dist.all_gather_into_tensor(out, desc)
+            return out
+        return desc
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = native.launch_count()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            d = fn(warmup + i)
+            if torch.is_tensor(d) and d.is_cuda:
+                gather(d)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), native.launch_count() - l0
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ms, launches = timed(step_resident, args.steps, args.warmup)
+    sampler.stop_flag = True
+    ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    e2e_steps = max(2, args.steps // 2)
+    if rank != 0:
+        return
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+    # ---- roofline of the dominant kernel family (rank 0, one instrumented step) ----
+    fam = kernel_profile(model, lambda: build_batch_device(*dev_batches[0], depth, 2))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    tf_peak = peaks.get('bf16_tflops_sustained', 1400.0)
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'measured' if peaks else 'fallback'
+    dom = max((k for k in fam if k != 'octree_build'), key=lambda k: fam[k]['ms'])
+    f = fam[dom]
+    if f['flop'] > 0:
+        ach = f['flop'] / (f['ms'] / 1e3) / 1e12
+        roof = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak,
+                'unit': 'TFLOP/s', 'frac': ach / tf_peak, 'traffic': None, 'peak_source': peak_src,
+                'launches_per_step': f['launches'], 'ms_per_step': f['ms']}
+    else:
+        ach = f['byte'] / (f['ms'] / 1e3) / 1e9
+        roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': ach / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'launches_per_step': f['launches'], 'ms_per_step': f['ms']}
+    tot = sum(v['ms'] for v in fam.values())
+    shares = {k: round(v['ms'] / tot, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])}
+    cpu = cpu_baseline(args, sample=args.cpu_sample) if not args.no_cpu else None
+    h2d = sum(c.nbytes for c in batches[0]) + 4 * (B + 1)
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': f'{args.config} cfg, {B} synthetic {P}-point submaps per step per GPU, '
+                               f'random-init weights (BASELINE.json configs[1])',
+                   'octree_depth': depth, 'l2': 'per-step working set (GBs of activations) >> 126 MB L2; '
+                                                'inputs cycle over 3 distinct batches',
+                   'parallelism': f'batch-sharded x{world}'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(B * 256 * 4), 'steps': e2e_steps},
+        'gpu_launches': int(launches), 'clocks': sampler.summary(), 'roofline': roof,
+        'kernel_time_shares': shares, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(out))
+
+
+def cpu_baseline(args, sample=4, steps=1, warmup=0):
+    """The oracle (CPU port of the reference path: per-submap octree build, merge,
+    neighbour construction, fp32 forward) on a bounded sample of the same workload."""
+    from oracle import model_ref as M, octree_ref as R
+    from hotformerloc_b200.config.presets import write_configs, TRAIN_PRESETS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = tempfile.mkdtemp(prefix='hfl_cfg_')
+    paths = write_configs(d, args.config, dataset_folder=d)
+    hp = M.HParams.from_cfg(paths['model_config'])
+    depth = TRAIN_PRESETS[args.config]['octree_depth']
+    shapes = json.load(open(os.path.join(ROOT, 'tests', 'golden', f'state_shapes_{args.config}.json')))
+    sd = M.synthetic_state_dict(shapes, mode='init')
+    times = []
+    for i in range(warmup + steps):
+        clouds = synthetic_batches(1, sample, args.points, seed0=5000 + i)[0]
+        t = time.perf_counter()
+        o = R.build_batch(clouds, depth)
+        M.forward(sd, o, hp)
+        if i >= warmup:
+            times.append(time.perf_counter() - t)
+    sec = float(np.mean(times))
+    return {'value': sample / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{sample} submaps of {args.points} points per step, {steps} step(s), '
+                      f'fp32, torch threads = {cores}', 'seconds_per_step': sec}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    cpu = cpu_baseline(args, sample=sample, steps=args.steps, warmup=min(args.warmup, 1))
+    out = {'impl': 'reference', 'metric': METRIC, 'value': cpu['value'], 'unit': UNIT,
+           'n_gpus': world, 'steps': args.steps, 'warmup': min(args.warmup, 1),
+           'ms_per_step': cpu['seconds_per_step'] * 1e3, 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': f'{args.config} cfg, {args.points}-point synthetic submaps, '
+                                  f'{sample} submaps per step (bounded sample of the 256-submap batch)'},
+           'cpu_baseline': cpu,
+           'e2e': {'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                   'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--config', default='oxford')
+    ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--points', type=int, default=4096)
+    ap.add_argument('--cpu-sample', type=int, default=4)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    try:
+        run_native(args, rank, world, device)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import native as N
 from .. import ops
 from ..octree import Octree
 
@@ -580,17 +581,17 @@ class _Engine:
         rt_local = [(np.arange(nwin[j], dtype=np.int64) * (K + 1)).astype(np.int32) for j in range(L)]
         parts = [rt_rows, ids, cu] + tok_off + rt_local
         sizes = [p.size for p in parts]
-        stage = torch.empty(sum(sizes), dtype=torch.int32, pin_memory=True)
+        stage = N.pinned.take(4 * sum(sizes)).view(torch.int32)
         o = 0
         for p in parts:
             stage[o:o + p.size] = torch.from_numpy(np.ascontiguousarray(p, dtype=np.int32))
             o += p.size
         devbuf = stage.to(octree.device, non_blocking=True)
+        N.pinned.mark()
         views, o = [], 0
         for s in sizes:
             views.append(devbuf[o:o + s])
             o += s
-        self._stage_keepalive = stage
         return dict(rt_rows=views[0], ids=views[1], cu=views[2], tok_off=views[3:3 + L],
                     rt_local=views[3 + L:3 + 2 * L], total_rt=total_rt,
                     max_len=int(tot.max()), num_windows=nws)

@@ -160,3 +160,31 @@ def stream():
 
 def launch_count() -> int:
     return int(lib().hfl_launch_count())
+
+
+class PinnedPool:
+    """Rotating pinned staging buffers: cudaHostAlloc is far too slow to pay per
+    batch.  A buffer is reused only after the H2D copy that read it has completed."""
+
+    def __init__(self, slots: int = 4):
+        self.slots = [None] * slots
+        self.i = 0
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        self.i = (self.i + 1) % len(self.slots)
+        slot = self.slots[self.i]
+        if slot is not None:
+            slot[1].synchronize()
+        if slot is None or slot[0].numel() < nbytes:
+            cap = max(1 << 16, 1 << (int(nbytes) - 1).bit_length())
+            slot = [torch.empty(cap, dtype=torch.uint8, pin_memory=True), torch.cuda.Event()]
+            self.slots[self.i] = slot
+        return slot[0][:nbytes]
+
+    def mark(self):
+        """Call after enqueuing the H2D copy that reads the buffer last taken."""
+        self.slots[self.i][1].record()
+
+
+pinned = PinnedPool()
+pinned_d2h = PinnedPool(slots=8)      # node-count read-backs (one per built octree)

@@ -69,17 +69,22 @@ class Octree:
         if min(sizes) < 1:
             raise ValueError('every submap needs at least one point')
         n = int(sum(sizes))
-        host = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
-        off = torch.zeros(B + 1, dtype=torch.int32, pin_memory=True)
+        # one pinned staging buffer: [points fp32 (n,3) | offsets int32 (B+1)] -> one H2D copy
+        nb_pts = 12 * n
+        stage = N.pinned.take(nb_pts + 4 * (B + 1))
+        host = stage[:nb_pts].view(torch.float32).view(n, 3)
+        off = stage[nb_pts:].view(torch.int32)
         o = 0
+        off[0] = 0
         for i, c in enumerate(clouds):
             host[o:o + sizes[i]] = torch.as_tensor(c, dtype=torch.float32)
             o += sizes[i]
             off[i + 1] = o
-        self._h2d_bytes = host.numel() * 4 + off.numel() * 4
-        dev = self.device
-        pts = host.to(dev, non_blocking=True)
-        offs = off.to(dev, non_blocking=True)
+        self._h2d_bytes = stage.numel()
+        devbuf = stage.to(self.device, non_blocking=True)
+        N.pinned.mark()
+        pts = devbuf[:nb_pts].view(torch.float32).view(n, 3)
+        offs = devbuf[nb_pts:].view(torch.int32)
         self._build_device(pts, offs, n, want_point_leaf, neigh)
 
     def _build_device(self, pts: torch.Tensor, offs: torch.Tensor, n: int,
@@ -128,8 +133,9 @@ class Octree:
         N.check(L.hfl_octree_build(N.ptr(pts), N.ptr(offs), C.byref(desc), N.ptr(ws), ws_bytes,
                                    N.stream()))
         # counts -> host (the only D2H of the build; shapes of every later tensor)
-        self._counts_host = torch.empty((D + 1, B + 2), dtype=torch.int32, pin_memory=True)
+        self._counts_host = N.pinned_d2h.take(4 * (D + 1) * (B + 2)).view(torch.int32).view(D + 1, B + 2)
         self._counts_host.copy_(self._counts_dev.view(D + 1, B + 2), non_blocking=True)
+        N.pinned_d2h.mark()
         self._ready = torch.cuda.Event()
         self._ready.record()
         self._pts_keepalive = (pts, offs, ws)
@@ -168,7 +174,7 @@ class Octree:
             return self
         self._ready.synchronize()
         B = self.batch_size
-        c = self._counts_host.to(torch.int64)
+        c = self._counts_host.to(torch.int64)        # copies out of the pinned staging slot
         self.batch_nnum_nempty = c[:, :B].clone()
         self.nnum_nempty = c[:, B].clone()
         self.nnum = c[:, B + 1].clone()
