@@ -49,42 +49,68 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-constexpr int WA_WARPS = 16;
-constexpr int WA_WARP_SMEM = 2 * AT_KEYS * AT_RS + AT_KEYS * 8;   // K, V, xyzb
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-__global__ void __launch_bounds__(WA_WARPS * 32, 1) k_window_attn(const WinAttnParams p) {
+// CTA = one window, warp = one head.  Per window the CTA builds, once for all heads, a
+// packed table  code[row][key] = 10-bit byte offsets into the (x | y | z) RPE sub-tables,
+// or 0x80000000 for a masked pair (different submap / padding key); each warp then runs
+// QK^T -> +bias -> softmax -> PV for its head with 3 LDS + 2 FADD of bias work per score.
+// With relay tokens the K window tokens form K/16 query tiles and the single relay-token
+// query row is handled by a short CUDA-core path instead of a 1/16-full MMA tile.
+template <int NT>
+__global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
+  constexpr int NTC = NT * 8;          // key columns covered
+  constexpr int PITCH = NTC + 4;       // code row pitch (words)
+  constexpr uint32_t MASKED = 0x80000000u;   // sign bit: offsets stay 0 (aligned, in range)
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int L = p.K + (p.hat ? 1 : 0);
-  const int num = 2 * p.bnd + 1;
-  const int tbl = 3 * num;
-  // RPE table transposed to [H][tbl] in smem
-  float* s_rpe = reinterpret_cast<float*>(smem);
-  const int rpe_bytes = p.rpe ? ((p.H * tbl * 4 + 15) & ~15) : 0;
-  if (p.rpe) {
-    for (int i = threadIdx.x; i < p.H * tbl; i += blockDim.x) {
-      int h = i / tbl, e = i - h * tbl;
-      s_rpe[i] = __ldg(p.rpe + (size_t)e * p.H + h) * LOG2E;
-    }
-  }
-  __syncthreads();
-  uint8_t* wbase = smem + rpe_bytes + (size_t)warp * WA_WARP_SMEM;
+  const int K = p.K, hat = p.hat, L = K + hat;
+  const int num = 2 * p.bnd + 1, sub = num + 1;          // sub-table pitch incl. a zero slot
+  float* s_rpe = reinterpret_cast<float*>(smem);                       // [H][3*sub]
+  const int rpe_bytes = (p.H * 3 * sub * 4 + 15) & ~15;
+  uint32_t* s_code = reinterpret_cast<uint32_t*>(smem + rpe_bytes);    // [K+1][PITCH]
+  const int code_bytes = ((K + 1) * PITCH * 4 + 15) & ~15;
+  short4* s_tok = reinterpret_cast<short4*>(smem + rpe_bytes + code_bytes);   // [NTC]
+  float* s_prob = reinterpret_cast<float*>(smem + rpe_bytes + code_bytes + NTC * 8);  // [H][NTC]
+  uint8_t* wbase = smem + rpe_bytes + code_bytes + NTC * 8 + p.H * NTC * 4 +
+                   (size_t)warp * (2 * NTC * AT_RS);
   uint8_t* sK = wbase;
-  uint8_t* sV = wbase + AT_KEYS * AT_RS;
-  short4* sT = reinterpret_cast<short4*>(wbase + 2 * AT_KEYS * AT_RS);
+  uint8_t* sV = wbase + NTC * AT_RS;
   const uint32_t sK_u = ptx::smem_u32(sK), sV_u = ptx::smem_u32(sV);
+
+  for (int i = threadIdx.x; i < p.H * 3 * sub; i += blockDim.x) {
+    const int h = i / (3 * sub), e = i - h * 3 * sub;
+    const int axis = e / sub, k = e - axis * sub;
+    s_rpe[i] = (p.rpe && k < num) ? __ldg(p.rpe + (size_t)(axis * num + k) * p.H + h) * LOG2E : 0.f;
+  }
+  const int h = warp;
+  const float* tabx = s_rpe + h * 3 * sub;
+  const float* taby = tabx + sub;
+  const float* tabz = taby + sub;
   const int C3 = 3 * p.C;
   const float sc = p.scale * LOG2E;
-  const int64_t items = (int64_t)p.n_win * p.H;
-  const int n_mt = (L + 15) / 16;
+  const uint32_t zero_off = (uint32_t)num * 4u;
+  const int n_mt = K / 16;
 
-  for (int64_t item = (int64_t)blockIdx.x * WA_WARPS + warp; item < items;
-       item += (int64_t)gridDim.x * WA_WARPS) {
-    const int w = (int)(item / p.H), h = (int)(item % p.H);
-    // ---- stage K, V (this head) and the token table of the window ----
-    for (int s = lane; s < AT_KEYS; s += 32) {
-      int64_t row = 0, tok = -1;
+  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x) {
+    __syncthreads();                              // previous window fully consumed
+    // ---- tokens of the window; K / V of this warp's head ----
+    for (int s = threadIdx.x; s < NTC; s += blockDim.x) {
+      short4 tk = make_short4(0, 0, 0, -2);
+      if (s < L) {
+        int64_t row, tok;
+        slot_row(p, w, s, row, tok);
+        tk = p.xyzb[tok >= 0 ? tok : (int64_t)w * K];      // relay token: id of the first token
+      }
+      s_tok[s] = tk;
+    }
+    for (int s = lane; s < NTC; s += 32) {
+      int64_t row = 0, tok;
       const bool ok = s < L;
       if (ok) slot_row(p, w, s, row, tok);
       const __nv_bfloat16* src = p.qkv + row * C3 + p.C + h * AT_HD;
@@ -92,124 +118,169 @@ __global__ void __launch_bounds__(WA_WARPS * 32, 1) k_window_attn(const WinAttnP
       ptx::cp_async16(sK_u + s * AT_RS + 16, src + 8, ok ? 16u : 0u);
       ptx::cp_async16(sV_u + s * AT_RS, src + p.C, ok ? 16u : 0u);
       ptx::cp_async16(sV_u + s * AT_RS + 16, src + p.C + 8, ok ? 16u : 0u);
-      short4 tk = make_short4(0, 0, 0, -2);
-      if (ok) {
-        if (tok >= 0) tk = p.xyzb[tok];
-        else { tk = p.xyzb[(int64_t)w * p.K]; tk.x = tk.y = tk.z = 0; }   // RT: id of first token
-      }
-      sT[s] = tk;
     }
     ptx::cp_async_commit();
+    __syncthreads();
+    // ---- packed mask / RPE-offset table: rows 0..K-1 = window tokens, row K = relay token ----
+    for (int e = threadIdx.x; e < (K + hat) * NTC; e += blockDim.x) {
+      const int r = e / NTC, j = e - r * NTC;
+      const bool rt_row = r == K;
+      const short4 ti = s_tok[rt_row ? 0 : r + hat];
+      const short4 tj = s_tok[j];
+      uint32_t code = MASKED;
+      if (j < L && ti.w == tj.w) {
+        if (rt_row || (hat && j == 0) || !p.rpe) {
+          code = zero_off | (zero_off << 10) | (zero_off << 20);
+        } else {
+          const uint32_t ox = (uint32_t)(min(max((int)ti.x - (int)tj.x, -p.bnd), p.bnd) + p.bnd) * 4u;
+          const uint32_t oy = (uint32_t)(min(max((int)ti.y - (int)tj.y, -p.bnd), p.bnd) + p.bnd) * 4u;
+          const uint32_t oz = (uint32_t)(min(max((int)ti.z - (int)tj.z, -p.bnd), p.bnd) + p.bnd) * 4u;
+          code = ox | (oy << 10) | (oz << 20);
+        }
+      }
+      s_code[r * PITCH + j] = code;
+    }
     ptx::cp_async_wait<0>();
-    __syncwarp();
-    const float* tab = s_rpe + h * tbl;
+    __syncthreads();
 
+    // ---- K/16 query tiles of window tokens ----
     for (int mt = 0; mt < n_mt; ++mt) {
-      const int i0 = mt * 16 + g, i1 = i0 + 8;
-      // ---- Q fragments straight from global ----
-      uint32_t qa[4] = {0u, 0u, 0u, 0u};
-      int64_t row0 = 0, row1 = 0, tk_;
-      if (i0 < L) {
-        slot_row(p, w, i0, row0, tk_);
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
-        qa[0] = __ldg(q + t); qa[2] = __ldg(q + t + 4);
+      const int r0 = mt * 16 + g, r1 = r0 + 8;               // token rows (slots r + hat)
+      int64_t row0, row1, tk_;
+      slot_row(p, w, r0 + hat, row0, tk_);
+      slot_row(p, w, r1 + hat, row1, tk_);
+      uint32_t qa[4];
+      {
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
+        qa[0] = __ldg(q0 + t); qa[2] = __ldg(q0 + t + 4);
+        qa[1] = __ldg(q1 + t); qa[3] = __ldg(q1 + t + 4);
       }
-      if (i1 < L) {
-        slot_row(p, w, i1, row1, tk_);
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
-        qa[1] = __ldg(q + t); qa[3] = __ldg(q + t + 4);
-      }
-      const short4 ti0 = sT[min(i0, AT_KEYS - 1)], ti1 = sT[min(i1, AT_KEYS - 1)];
-      const bool rt0 = p.hat && i0 == 0;      // relay-token row: no RPE
-      // ---- S = Q K^T ----
-      float s[AT_NT][4];
+      float s[NT][4];
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < AT_NT; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
         uint32_t kb[2];
         const uint8_t* kr = sK + (nt * 8 + g) * AT_RS + t * 4;
         kb[0] = *reinterpret_cast<const uint32_t*>(kr);
         kb[1] = *reinterpret_cast<const uint32_t*>(kr + 16);
         ptx::mma16816(s[nt], qa, kb);
-      }
-      // ---- bias: submap mask + relative position ----
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+        const uint2 c0 = *reinterpret_cast<const uint2*>(s_code + r0 * PITCH + nt * 8 + 2 * t);
+        const uint2 c1 = *reinterpret_cast<const uint2*>(s_code + r1 * PITCH + nt * 8 + 2 * t);
+        const uint32_t cc[4] = {c0.x, c0.y, c1.x, c1.y};
 #pragma unroll
-      for (int nt = 0; nt < AT_NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = nt * 8 + 2 * t + e;
-          const short4 tj = sT[j];
-          const bool rtj = p.hat && j == 0;
-          float b0 = 0.f, b1 = 0.f;
-          if (p.rpe) {
-            if (!rtj) {
-              if (!rt0) {
-                int dx = min(max((int)ti0.x - (int)tj.x, -p.bnd), p.bnd) + p.bnd;
-                int dy = min(max((int)ti0.y - (int)tj.y, -p.bnd), p.bnd) + p.bnd + num;
-                int dz = min(max((int)ti0.z - (int)tj.z, -p.bnd), p.bnd) + p.bnd + 2 * num;
-                b0 = tab[dx] + tab[dy] + tab[dz];
-              }
-              int dx = min(max((int)ti1.x - (int)tj.x, -p.bnd), p.bnd) + p.bnd;
-              int dy = min(max((int)ti1.y - (int)tj.y, -p.bnd), p.bnd) + p.bnd + num;
-              int dz = min(max((int)ti1.z - (int)tj.z, -p.bnd), p.bnd) + p.bnd + 2 * num;
-              b1 = tab[dx] + tab[dy] + tab[dz];
-            }
-          }
-          const bool v0 = (j < L) && (i0 < L) && (tj.w == ti0.w);
-          const bool v1 = (j < L) && (i1 < L) && (tj.w == ti1.w);
-          s[nt][e] = v0 ? s[nt][e] * sc + b0 : -INFINITY;
-          s[nt][2 + e] = v1 ? s[nt][2 + e] * sc + b1 : -INFINITY;
-          mx0 = fmaxf(mx0, s[nt][e]);
-          mx1 = fmaxf(mx1, s[nt][2 + e]);
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t c = cc[e];
+          const float bias = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(tabx) + (c & 1023u)) +
+                             *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(taby) + ((c >> 10) & 1023u)) +
+                             *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(tabz) + ((c >> 20) & 1023u));
+          s[nt][e] = c == MASKED ? -INFINITY : fmaf(s[nt][e], sc, bias);
         }
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      if (mx0 == -INFINITY) mx0 = 0.f;
-      if (mx1 == -INFINITY) mx1 = 0.f;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < AT_NT; ++nt) {
-        s[nt][0] = exp2f(s[nt][0] - mx0); s[nt][1] = exp2f(s[nt][1] - mx0);
-        s[nt][2] = exp2f(s[nt][2] - mx1); s[nt][3] = exp2f(s[nt][3] - mx1);
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = fast_exp2(s[nt][0] - mx0); s[nt][1] = fast_exp2(s[nt][1] - mx0);
+        s[nt][2] = fast_exp2(s[nt][2] - mx1); s[nt][3] = fast_exp2(s[nt][3] - mx1);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
       }
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      // ---- O = P V ----
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int kt = 0; kt < AT_NT / 2; ++kt) {
+      for (int kt = 0; kt < (NT + 1) / 2; ++kt) {
         uint32_t pa[4];
         pa[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
         pa[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
-        pa[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-        pa[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+        if (2 * kt + 1 < NT) {
+          pa[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+          pa[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+        } else {
+          pa[2] = pa[3] = 0u;
+        }
         uint32_t vb[4];
         const int mi = lane >> 3;
-        const uint32_t va = sV_u + (kt * 16 + (mi & 1) * 8 + (lane & 7)) * AT_RS + (mi >> 1) * 16;
-        ptx::ldmatrix_x4_trans(vb, va);
+        int key = kt * 16 + (mi & 1) * 8 + (lane & 7);
+        key = key < NTC ? key : 0;                  // second half of an odd last tile: P == 0
+        ptx::ldmatrix_x4_trans(vb, sV_u + key * AT_RS + (mi >> 1) * 16);
         uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
         ptx::mma16816(o[0], pa, b0);
         ptx::mma16816(o[1], pa, b1);
       }
-      const float r0 = l0 > 0.f ? 1.f / l0 : 0.f, r1 = l1 > 0.f ? 1.f / l1 : 0.f;
-      if (i0 < L) {
-        uint32_t* d = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
-        d[t] = pack_bf16(o[0][0] * r0, o[0][1] * r0);
-        d[t + 4] = pack_bf16(o[1][0] * r0, o[1][1] * r0);
-      }
-      if (i1 < L) {
-        uint32_t* d = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
-        d[t] = pack_bf16(o[0][2] * r1, o[0][3] * r1);
-        d[t + 4] = pack_bf16(o[1][2] * r1, o[1][3] * r1);
-      }
+      // every row has at least itself unmasked, so l > 0
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
+      uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
+      d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
+      d0[t + 4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
+      d1[t] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
+      d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
     }
-    __syncwarp();
+    // ---- the relay-token query row (no RPE): lanes over keys, then lanes over (dim, half) ----
+    if (hat) {
+      const int64_t rowq = (int64_t)w * (K + 1);
+      float q[AT_HD];
+      {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + rowq * C3 + h * AT_HD);
+        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+        const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+          q[2 * i] = f.x; q[2 * i + 1] = f.y;
+        }
+      }
+      float sj[(NTC + 31) / 32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < (NTC + 31) / 32; ++u) {
+        const int j = lane + 32 * u;
+        float a = -INFINITY;
+        if (j < NTC && s_code[K * PITCH + j] != MASKED) {
+          const uint4* kp = reinterpret_cast<const uint4*>(sK + j * AT_RS);
+          const uint4 ka = kp[0], kb = kp[1];
+          const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+          a = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+            a = fmaf(q[2 * i], f.x, a);
+            a = fmaf(q[2 * i + 1], f.y, a);
+          }
+          a *= sc;
+        }
+        sj[u] = a;
+        mx = fmaxf(mx, a);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float l = 0.f;
+      float* pr = s_prob + h * NTC;
+#pragma unroll
+      for (int u = 0; u < (NTC + 31) / 32; ++u) {
+        const int j = lane + 32 * u;
+        const float e = fast_exp2(sj[u] - mx);
+        l += e;
+        if (j < NTC) pr[j] = e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      __syncwarp();
+      const int d = lane & 15, half = lane >> 4;
+      float acc = 0.f;
+      for (int j = half; j < L; j += 2)
+        acc = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sV + j * AT_RS + d * 2)), acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
+    }
   }
 }
 
@@ -374,27 +445,38 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   cudaStream_t st = (cudaStream_t)stream_;
   if (n_win == 0) return HFL_OK;
   HFL_CHECK_ARG(qkv && out && xyzb, "null argument");
-  HFL_CHECK_ARG(C == H * AT_HD, "head_dim must be 16");
-  HFL_CHECK_ARG(K + (hat ? 1 : 0) <= AT_KEYS, "window (+relay token) must fit 80 keys");
+  HFL_CHECK_ARG(C == H * AT_HD && H <= 16, "head_dim must be 16, at most 16 heads");
+  HFL_CHECK_ARG(K % 16 == 0 && K + (hat ? 1 : 0) <= AT_KEYS, "window must be a multiple of 16 and (+relay token) fit 80 keys");
   HFL_CHECK_ARG(dil >= 1 && (!hat || dil == 1), "dilation is not used with relay tokens");
   HFL_CHECK_ARG(n_win % dil == 0, "window count must be a multiple of the dilation");
+  HFL_CHECK_ARG(bnd >= 0 && (2 * bnd + 1) * 4 < 1024, "RPE bound too large for the packed offsets");
   WinAttnParams p;
   p.qkv = (const __nv_bfloat16*)qkv; p.out = (__nv_bfloat16*)out; p.xyzb = (const short4*)xyzb;
   p.rpe = rpe; p.n_win = (int)n_win; p.H = H; p.C = C; p.K = K; p.dil = dil; p.hat = hat;
   p.bnd = bnd; p.scale = scale;
-  const int tbl = 3 * (2 * bnd + 1);
-  const int rpe_bytes = rpe ? ((H * tbl * 4 + 15) & ~15) : 0;
-  const int smem = rpe_bytes + WA_WARPS * WA_WARP_SMEM;
-  HFL_CHECK_ARG(smem <= 227 * 1024, "RPE table too large for shared memory");
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    HFL_CUDA(cudaFuncSetAttribute(k_window_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
+  const int L = K + (hat ? 1 : 0);
+  const int NT = (L + 7) / 8, NTC = NT * 8, PITCH = NTC + 4;
+  const int sub = 2 * bnd + 2;
+  const int smem = ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + NTC * 8 +
+                   H * NTC * 4 + H * 2 * NTC * AT_RS;
+  HFL_CHECK_ARG(smem <= 227 * 1024, "window attention tables exceed shared memory");
+  int grid = (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
+#define HFL_WA_CASE(NT_)                                                                          \
+  case NT_: {                                                                                     \
+    static int smem_set = 0;                                                                      \
+    if (smem > smem_set) {                                                                        \
+      HFL_CUDA(cudaFuncSetAttribute(k_window_attn<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      smem_set = smem;                                                                            \
+    }                                                                                             \
+    HFL_LAUNCH((k_window_attn<NT_><<<grid, H * 32, smem, st>>>(p)));                              \
+    break;                                                                                        \
   }
-  const int64_t items = n_win * H;
-  int grid = (int)ceil_div(items, WA_WARPS);
-  if (grid > kSMs) grid = kSMs;
-  HFL_LAUNCH((k_window_attn<<<grid, WA_WARPS * 32, smem, st>>>(p)));
+  switch (NT) {
+    HFL_WA_CASE(2) HFL_WA_CASE(3) HFL_WA_CASE(4) HFL_WA_CASE(5) HFL_WA_CASE(6) HFL_WA_CASE(7)
+    HFL_WA_CASE(8) HFL_WA_CASE(9) HFL_WA_CASE(10)
+    default: return fail(HFL_ERR_UNSUPPORTED, "unsupported window size%s (%lld)", "", (long long)K);
+  }
+#undef HFL_WA_CASE
   return HFL_OK;
 }
 

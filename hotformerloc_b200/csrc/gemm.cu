@@ -7,10 +7,11 @@
 // * KD == 27 or 8         : ocnn OctreeConv as an implicit GEMM -- the im2col buffer of
 //                           the reference (rows x kdim x Cin) is never materialised;
 //                           rows are gathered straight into the swizzled smem operand.
-// Persistent, warp-specialised CTA (288 threads, 1 CTA / SM):
-//   warps 0-3  epilogue   (TMEM lane quadrant = warp id; thread == output row)
-//   warp  4    TMEM alloc + single-thread tcgen05.mma issue (M=128, N=block_n, K=16)
-//   warps 5-8  A producers: thread == tile row, 8 x 16 B cp.async (zero-fill for
+// Persistent, warp-specialised CTA (416 threads, 1 CTA / SM):
+//   warps 0-7  epilogue   (TMEM lane quadrant = warp % 4, column half = warp / 4;
+//              thread == output row)
+//   warp  8    TMEM alloc + single-thread tcgen05.mma issue (M=128, N=block_n, K=16)
+//   warps 9-12 A producers: thread == tile row, 8 x 16 B cp.async (zero-fill for
 //              neigh < 0 / tail rows) into the 128B-swizzled K-major layout;
 //              first producer thread also issues the TMA load of the weight tile.
 // 4-stage smem ring (A 16 KB + B <= 32 KB per stage), double-buffered TMEM accumulators
@@ -27,18 +28,25 @@ namespace hfl {
 
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
-constexpr int G_STAGES = 4;
-constexpr int G_LAG = 2;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;    // 16 KB
 constexpr int G_B_BYTES = 256 * G_BK * 2;     // 32 KB (block_n <= 256)
-constexpr int G_THREADS = 288;
-constexpr int G_SMEM = G_STAGES * (G_A_BYTES + G_B_BYTES) + 256 + 1024;
+constexpr int G_THREADS = 416;       // 8 epilogue + 1 MMA + 4 producer warps
+constexpr int G_W_MMA = 8, G_W_PROD = 9;
+// streaming mode: 4 stages of (A 16 KB + B 32 KB); weight-stationary mode (Ktot*block_n*2 <=
+// 128 KB): the whole W tile lives in smem for the lifetime of the CTA and 4 stages of A stream.
+constexpr int G_STAGES_STREAM = 4, G_LAG_STREAM = 2;
+constexpr int G_STAGES_WS = 4, G_LAG_WS = 2;
+constexpr int G_WS_W_BYTES = 128 * 1024;
+constexpr int G_PIPE_BYTES = 192 * 1024;      // = 4*(16+32) KB (stream) = 4*16 KB + 128 KB (WS)
+constexpr int G_STAGE_BYTES = 8 * 2048;       // per epilogue warp: 32 rows x 64 B transpose buffer
+constexpr int G_SMEM = G_PIPE_BYTES + G_STAGE_BYTES + 256 + 2048 + 1024;   // + barriers + LN exchange + align
 
 struct GemmParams {
   const __nv_bfloat16* A;   // [rows_A, Cin]
   const int32_t* idx;       // [M, KD] row gather table or NULL (identity, KD == 1)
   int M, N, KD, Cin;        // Ktot = KD * Cin
   int block_n, n_tiles;
+  int ws;                   // weight-stationary mode
   // epilogue
   const float* bias;        // [N] or NULL
   const float* res;         // fp32 residual, row-mapped like out_v, or NULL
@@ -55,64 +63,164 @@ struct GemmParams {
   float ln_eps;
 };
 
-__device__ __forceinline__ float gelu_erf(float v) {
-  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)).  erf(a) = sign(a) (1 - exp(t P(t))) with a degree-6
+// polynomial (one MUFU.EX2 + 9 FMA per element; the epilogue is MUFU/issue bound, so the
+// division + exp of the textbook forms matter).  |GELU error| <= 2e-6 over [-8, 8]
+// (checked against scipy.special.erf), i.e. < 6 % of one bf16 ulp of the stored activation.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float a = x * 0.70710678118654752f;
+  const float t = fabsf(a), s = a * a;
+  float r = fmaf(-1.72853470e-5f, t, 3.83197126e-4f);
+  const float u = fmaf(-3.88396438e-3f, t, 2.42546219e-2f);
+  r = fmaf(r, s, u);
+  r = fmaf(r, t, -1.06777877e-1f);
+  r = fmaf(r, t, -6.34846687e-1f);
+  r = fmaf(r, t, -1.28717512e-1f);
+  r = fmaf(r, t, -t);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * 1.4426950408889634f));
+  return 0.5f * x * (1.0f + copysignf(1.0f - e, x));
 }
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
+// ---- coalesced epilogue I/O --------------------------------------------------------
+// TMEM hands every thread one output ROW; a naive store makes each warp instruction touch
+// 32 rows x 16 B (half-empty sectors, 2x the L2 write transactions).  Each epilogue warp
+// therefore owns a 32-row x 64-byte transpose buffer (XOR-swizzled, conflict-free both
+// ways): threads deposit their row segment, then lanes (row = lane/4 + 8i, seg = lane%4)
+// move full 64-byte row segments to / from global memory.
+__device__ __forceinline__ uint32_t stage_addr(uint32_t stage, int row, int seg) {
+  return stage + (uint32_t)row * 64u + (uint32_t)((seg ^ ((row >> 1) & 3)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+// one 64-byte-per-row unit: this thread's 16 words w[0..15] -> global rows orow (per lane)
+__device__ __forceinline__ void store_unit(uint32_t stage, int lane, const uint32_t* w,
+                                           char* gbase, int32_t orow, size_t row_bytes,
+                                           size_t col_byte) {
+  __syncwarp();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t w[4];
+  for (int q = 0; q < 4; ++q)
+    sts128(stage_addr(stage, lane, q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 p = __floats2bfloat162_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-      w[j] = *reinterpret_cast<uint32_t*>(&p);
-    }
-    d4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int i = 0; i < 4; ++i) {
+    const int row = (lane >> 2) + 8 * i, seg = lane & 3;
+    const uint4 v = lds128(stage_addr(stage, row, seg));
+    const int32_t orr = __shfl_sync(0xffffffffu, orow, row);
+    if (orr >= 0)
+      *reinterpret_cast<uint4*>(gbase + (size_t)orr * row_bytes + col_byte + seg * 16) = v;
   }
 }
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
+__device__ __forceinline__ void store_f32x32(uint32_t stage, int lane, float* base, int32_t orow,
+                                             int ld, int col, const float (&v)[32]) {
+  uint32_t w[16];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int u = 0; u < 2; ++u) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(v[u * 16 + j]);
+    store_unit(stage, lane, w, reinterpret_cast<char*>(base), orow, (size_t)ld * 4,
+               (size_t)(col + u * 16) * 4);
+  }
+}
+__device__ __forceinline__ void store_bf16x32(uint32_t stage, int lane, __nv_bfloat16* base,
+                                              int32_t orow, int ld, int col, const float (&v)[32]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  store_unit(stage, lane, w, reinterpret_cast<char*>(base), orow, (size_t)ld * 2, (size_t)col * 2);
+}
+// coalesced fetch of a 32-row x 32-column fp32 chunk: issue (global -> regs) ...
+__device__ __forceinline__ void res_issue(const float* base, int32_t orow, int ld, int col, int lane,
+                                          uint4 (&buf)[8]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = (lane >> 2) + 8 * i, seg = lane & 3;
+      const int32_t orr = __shfl_sync(0xffffffffu, orow, row);
+      buf[u * 4 + i] = orr >= 0 ? *reinterpret_cast<const uint4*>(base + (size_t)orr * ld + col + u * 16 + seg * 4)
+                                : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+// ... then transpose through the staging buffer and add to this thread's row
+__device__ __forceinline__ void res_add(uint32_t stage, int lane, const uint4 (&buf)[8], float (&v)[32]) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = (lane >> 2) + 8 * i, seg = lane & 3;
+      const uint4 b = buf[u * 4 + i];
+      sts128(stage_addr(stage, row, seg), b.x, b.y, b.z, b.w);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 b = lds128(stage_addr(stage, lane, q));
+      v[u * 16 + 4 * q] += __uint_as_float(b.x);
+      v[u * 16 + 4 * q + 1] += __uint_as_float(b.y);
+      v[u * 16 + 4 * q + 2] += __uint_as_float(b.z);
+      v[u * 16 + 4 * q + 3] += __uint_as_float(b.w);
+    }
+  }
 }
 
+template <bool WS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  constexpr int G_STAGES = WS ? G_STAGES_WS : G_STAGES_STREAM;
+  constexpr int G_LAG = WS ? G_LAG_WS : G_LAG_STREAM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sA = base;
-  const uint32_t sB = base + G_STAGES * G_A_BYTES;
-  const uint32_t sBar = sB + G_STAGES * G_B_BYTES;
+  const uint32_t sB = base + G_STAGES * G_A_BYTES;      // stream: B ring; WS: resident W tile
+  const uint32_t sStage = base + G_PIPE_BYTES;          // epilogue transpose buffers
+  const uint32_t sBar = sStage + G_STAGE_BYTES;
   const uint32_t bar_full = sBar;                       // G_STAGES x 8 B
   const uint32_t bar_empty = sBar + 8 * G_STAGES;       // G_STAGES x 8 B
   const uint32_t bar_tfull = sBar + 16 * G_STAGES;      // 2 x 8 B
   const uint32_t bar_tempty = bar_tfull + 16;           // 2 x 8 B
-  const uint32_t s_tmem = bar_tempty + 16;              // 4 B
+  const uint32_t bar_w = bar_tempty + 16;               // 8 B (WS: W tile landed)
+  const uint32_t s_tmem = bar_w + 8;                    // 4 B
+  float2* s_ln = reinterpret_cast<float2*>(smem + (sBar + 256 - base));   // [2 halves][128 rows]
   volatile uint32_t* tmem_ptr_s =
       reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + G_BM - 1) / G_BM;
-  const int total_tiles = m_tiles * p.n_tiles;
   const int k_blocks = (p.KD * p.Cin) / G_BK;
   const int BN = p.block_n;
+  // tile schedule.  stream: t = m_blk * n_tiles + n_blk, CTAs stride over t.
+  // WS: the CTA owns one n_blk (its W tile) and strides over the M tiles.
+  const int t_begin = WS ? (int)(blockIdx.x / p.n_tiles) : (int)blockIdx.x;
+  const int t_step = WS ? (int)(gridDim.x / p.n_tiles) : (int)gridDim.x;
+  const int t_end = WS ? m_tiles : m_tiles * p.n_tiles;
+  const int ws_n_blk = blockIdx.x % p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, 128 + 1);
+      ptx::mbar_init(bar_full + 8 * s, WS ? 128 : 128 + 1);
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
+    ptx::mbar_init(bar_w, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_tfull + 8 * a, 1);
-      ptx::mbar_init(bar_tempty + 8 * a, 4);
+      ptx::mbar_init(bar_tempty + 8 * a, 8);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == G_W_MMA) {
     ptx::tmem_alloc(s_tmem, 512);
     ptx::tmem_relinquish();
   }
@@ -121,40 +229,48 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp >= 5) {
+  if (warp >= G_W_PROD) {
     // ===================== A producers (+ TMA for W) =====================
-    const int r = (warp - 5) * 32 + lane;                // tile row
-    const bool tma_thread = (warp == 5 && lane == 0);
+    // 128 threads; thread = (16-byte chunk c of the 128-byte K-block row, rows rbase + 16 i):
+    // 8 consecutive lanes fetch one full 128-byte line -> every cp.async is sector-complete.
+    const int pt = (warp - G_W_PROD) * 32 + lane;
+    const int c = pt & 7, rbase = pt >> 3;
+    const bool tma_thread = (pt == 0);
     if (tma_thread) ptx::prefetch_tmap(&tmap_w);
     const uint32_t b_bytes = (uint32_t)BN * G_BK * 2;
     uint32_t g = 0;                                      // k-block counter (ring position)
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m_blk = t / p.n_tiles, n_blk = t % p.n_tiles;
-      const int m = m_blk * G_BM + r;
-      const bool row_ok = m < p.M;
-      const int32_t* idx_row = (p.idx && row_ok) ? p.idx + (size_t)m * p.KD : nullptr;
-      int cached_kk = -1;
-      int64_t cached_src = -1;
+    if (WS && tma_thread) {                              // resident W tile: one shot
+      ptx::mbar_arrive_expect_tx(bar_w, (uint32_t)k_blocks * b_bytes);
+      for (int kb = 0; kb < k_blocks; ++kb)
+        ptx::tma_load_2d(sB + kb * b_bytes, &tmap_w, bar_w, kb * G_BK, ws_n_blk * BN);
+    }
+    for (int t = t_begin; t < t_end; t += t_step) {
+      const int m_blk = WS ? t : t / p.n_tiles, n_blk = WS ? ws_n_blk : t % p.n_tiles;
+      const int m0 = m_blk * G_BM + rbase;
       for (int kb = 0; kb < k_blocks; ++kb, ++g) {
         const uint32_t s = g % G_STAGES, ph = (g / G_STAGES) & 1;
+        const int kglob = kb * G_BK + c * 8;
+        const int kk = kglob / p.Cin;
+        const int ch = kglob - kk * p.Cin;
+        // gather rows for this K-block (issued before the slot wait to overlap its latency)
+        int64_t src_row[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + 16 * i;
+          src_row[i] = m >= p.M ? -1 : (p.idx ? (int64_t)__ldg(p.idx + (size_t)m * p.KD + kk) : (int64_t)m);
+        }
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        if (tma_thread) {
+        if (!WS && tma_thread) {
           ptx::mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
           ptx::tma_load_2d(sB + s * G_B_BYTES, &tmap_w, bar_full + 8 * s, kb * G_BK, n_blk * BN);
         }
-        const uint32_t dst_row = sA + s * G_A_BYTES + (uint32_t)r * 128u;
+        const uint32_t dst = sA + s * G_A_BYTES;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int kglob = kb * G_BK + c * 8;
-          const int kk = kglob / p.Cin;
-          const int ch = kglob - kk * p.Cin;
-          if (kk != cached_kk) {
-            cached_kk = kk;
-            cached_src = !row_ok ? -1 : (idx_row ? (int64_t)__ldg(idx_row + kk) : (int64_t)m);
-          }
-          const bool ok = cached_src >= 0;
-          const __nv_bfloat16* src = p.A + (ok ? (size_t)cached_src * p.Cin + ch : 0);
-          ptx::cp_async16(dst_row + (uint32_t)((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        for (int i = 0; i < 8; ++i) {
+          const int r = rbase + 16 * i;
+          const bool ok = src_row[i] >= 0;
+          const __nv_bfloat16* src = p.A + (ok ? (size_t)src_row[i] * p.Cin + ch : 0);
+          ptx::cp_async16(dst + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         }
         ptx::cp_async_commit();
         if (g >= G_LAG) {
@@ -168,12 +284,16 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     ptx::fence_proxy_async();
     const uint32_t first = g >= G_LAG ? g - G_LAG : 0;
     for (uint32_t q = first; q < g; ++q) ptx::mbar_arrive(bar_full + 8 * (q % G_STAGES));
-  } else if (warp == 4) {
+  } else if (warp == G_W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(G_BM, BN);
       uint32_t g = 0, it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if (WS) {
+        ptx::mbar_wait(bar_w, 0);
+        ptx::tc_fence_after();
+      }
+      for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const uint32_t acc = it & 1, aph = (it >> 1) & 1;
         ptx::mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
         ptx::tc_fence_after();
@@ -183,7 +303,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
           ptx::mbar_wait(bar_full + 8 * s, ph);
           ptx::tc_fence_after();
           const uint64_t ad = ptx::umma_desc_sw128(sA + s * G_A_BYTES);
-          const uint64_t bd = ptx::umma_desc_sw128(sB + s * G_B_BYTES);
+          const uint64_t bd = ptx::umma_desc_sw128(WS ? sB + kb * (BN * G_BK * 2) : sB + s * G_B_BYTES);
 #pragma unroll
           for (int k = 0; k < G_BK / 16; ++k)
             ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
@@ -194,24 +314,31 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 0-3) =====================
-    const int r = warp * 32 + lane;
+    // ===================== epilogue (warps 0-7) =====================
+    // warp % 4 = TMEM lane quadrant (hardware rule), warp / 4 = column half of the tile.
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const int HB = BN >> 1;                              // columns per half (multiple of 32)
+    const int cbeg = half * HB;
+    const uint32_t stage = sStage + (uint32_t)warp * 2048u;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int m_blk = t / p.n_tiles, n_blk = t % p.n_tiles;
+    for (int t = t_begin; t < t_end; t += t_step, ++it) {
+      const int m_blk = WS ? t : t / p.n_tiles, n_blk = WS ? ws_n_blk : t % p.n_tiles;
       const uint32_t acc = it & 1, aph = (it >> 1) & 1;
       const int m = m_blk * G_BM + r;
       const int n0 = n_blk * BN;
+      int32_t orow = -1;
+      if (m < p.M) orow = p.out_rows ? __ldg(p.out_rows + m) : m;
+      const int32_t yrow = p.y_mapped ? orow : (m < p.M ? m : -1);
+      const bool do_ln = p.ln_g != nullptr;
+      const bool has_res = p.res != nullptr;
+      uint4 rbuf[8];
+      if (has_res) res_issue(p.res, orow, p.N, n0 + cbeg, lane, rbuf);   // first residual chunk
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 256;
-      int64_t orow = -1;
-      if (m < p.M) orow = p.out_rows ? (int64_t)__ldg(p.out_rows + m) : (int64_t)m;
-      const bool live = orow >= 0;
-      const int64_t yrow = p.y_mapped ? orow : (int64_t)m;
-      const bool do_ln = p.ln_g != nullptr;
-      float sum = 0.f;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + cbeg;
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;              // shifted sums for LayerNorm
+      for (int c0 = 0; c0 < HB; c0 += 32) {
         uint32_t raw32[32];
         ptx::tmem_ld32(taddr + c0, raw32);
         ptx::tmem_ld_wait();
@@ -221,53 +348,53 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
         if (p.bias) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + q);
+            float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cbeg + c0) + q);
             v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
           }
         }
-        if (p.res && live) {
-          const float4* rp = reinterpret_cast<const float4*>(p.res + orow * p.N + n0 + c0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 b = rp[q];
-            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-          }
+        if (has_res) {
+          res_add(stage, lane, rbuf, v);
+          if (c0 + 32 < HB) res_issue(p.res, orow, p.N, n0 + cbeg + c0 + 32, lane, rbuf);
         }
         if (p.act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
-        if (live) {
-          if (p.out_v_f32) store_f32x32(p.out_v_f32 + orow * p.N + n0 + c0, v);
-          if (p.out_v_bf16) store_bf16x32(p.out_v_bf16 + orow * p.N + n0 + c0, v);
-        }
+        if (p.out_v_f32) store_f32x32(stage, lane, p.out_v_f32, orow, p.N, n0 + cbeg + c0, v);
+        if (p.out_v_bf16) store_bf16x32(stage, lane, p.out_v_bf16, orow, p.N, n0 + cbeg + c0, v);
         if (do_ln) {
+          if (c0 == 0) shift = v[0];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { sum += v[j]; raw32[j] = __float_as_uint(v[j]); }
+          for (int j = 0; j < 32; ++j) {
+            const float d = v[j] - shift;
+            s1 += d; s2 += d * d;
+            raw32[j] = __float_as_uint(v[j]);
+          }
           ptx::tmem_st32(taddr + c0, raw32);
         }
       }
       if (do_ln) {
+        // per-half (mean, M2) -> exchange with the other column half of this row -> full-row stats
+        const float nh = (float)HB;
+        const float mean_h = shift + s1 / nh;
+        const float m2_h = s2 - s1 * s1 / nh;
+        s_ln[half * 128 + r] = make_float2(mean_h, m2_h);
         ptx::tmem_st_wait();
-        const float mean = sum / (float)BN;
-        float ss = 0.f;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t raw32[32];
-          ptx::tmem_ld32(taddr + c0, raw32);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { float d = __uint_as_float(raw32[j]) - mean; ss += d * d; }
-        }
-        const float rstd = rsqrtf(ss / (float)BN + p.ln_eps);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float2 o = s_ln[(half ^ 1) * 128 + r];
+        const float delta = o.x - mean_h;
+        const float mean = mean_h + 0.5f * delta;
+        const float var = (m2_h + o.y + delta * delta * nh * 0.5f) / (2.f * nh);
+        const float rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+        for (int c0 = 0; c0 < HB; c0 += 32) {
           uint32_t raw32[32];
           ptx::tmem_ld32(taddr + c0, raw32);
           ptx::tmem_ld_wait();
           float y[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + c0) + q);
-            float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + c0) + q);
+            float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + cbeg + c0) + q);
+            float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + cbeg + c0) + q);
             y[4 * q] = (__uint_as_float(raw32[4 * q]) - mean) * rstd * gm.x + bt.x;
             y[4 * q + 1] = (__uint_as_float(raw32[4 * q + 1]) - mean) * rstd * gm.y + bt.y;
             y[4 * q + 2] = (__uint_as_float(raw32[4 * q + 2]) - mean) * rstd * gm.z + bt.z;
@@ -277,11 +404,11 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
           }
-          if (yrow >= 0 && m < p.M) {
-            if (p.out_y_f32) store_f32x32(p.out_y_f32 + yrow * p.N + c0, y);
-            if (p.out_y_bf16) store_bf16x32(p.out_y_bf16 + yrow * p.N + c0, y);
-          }
+          if (p.out_y_f32) store_f32x32(stage, lane, p.out_y_f32, yrow, p.N, cbeg + c0, y);
+          if (p.out_y_bf16) store_bf16x32(stage, lane, p.out_y_bf16, yrow, p.N, cbeg + c0, y);
         }
+        // the exchange slot is rewritten only after both halves passed the next bar.sync
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -290,7 +417,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == G_W_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -330,13 +457,13 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
   cudaStream_t st = (cudaStream_t)stream_;
   if (M == 0) return HFL_OK;
   HFL_CHECK_ARG(A && W && M > 0 && M < (1ll << 31), "bad A/W/M");
-  HFL_CHECK_ARG(N >= 32 && N % 32 == 0 && N <= 4096, "N must be a multiple of 32");
+  HFL_CHECK_ARG(N >= 64 && N % 64 == 0 && N <= 4096, "N must be a multiple of 64");
   HFL_CHECK_ARG(KD >= 1 && Cin >= 8 && Cin % 8 == 0, "Cin must be a multiple of 8");
   HFL_CHECK_ARG(((int64_t)KD * Cin) % G_BK == 0, "KD*Cin must be a multiple of 64");
   HFL_CHECK_ARG(Cin % G_BK == 0 || G_BK % Cin == 0, "Cin must divide or be a multiple of 64");
   HFL_CHECK_ARG(idx != nullptr || KD == 1, "KD > 1 needs a gather table");
   const int n_tiles = (N + 255) / 256;
-  HFL_CHECK_ARG(N % n_tiles == 0 && (N / n_tiles) % 32 == 0, "N not tileable");
+  HFL_CHECK_ARG(N % n_tiles == 0 && (N / n_tiles) % 64 == 0, "N must split into tiles that are multiples of 64");
   const int block_n = N / n_tiles;
   HFL_CHECK_ARG(!ln_g || (n_tiles == 1 && ln_b), "LayerNorm epilogue needs N <= 256");
   PFN_encodeTiled enc = get_encode();
@@ -359,12 +486,21 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
   p.out_y_bf16 = (__nv_bfloat16*)out_y_bf16; p.out_rows = out_rows; p.ln_eps = 1e-5f;
   static bool attr_set = false;
   if (!attr_set) {
-    HFL_CUDA(cudaFuncSetAttribute(k_gather_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    HFL_CUDA(cudaFuncSetAttribute(k_gather_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    HFL_CUDA(cudaFuncSetAttribute(k_gather_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     attr_set = true;
   }
-  const int64_t tiles = ceil_div(M, G_BM) * n_tiles;
-  const int grid = (int)(tiles < kSMs ? tiles : kSMs);
-  HFL_LAUNCH((k_gather_gemm<<<grid, G_THREADS, G_SMEM, st>>>(tmap, p)));
+  const int64_t m_tiles = ceil_div(M, G_BM);
+  // weight-stationary when the W tile fits next to the A ring and every CTA gets >= 2 M tiles
+  p.ws = ((int64_t)Ktot * block_n * 2 <= G_WS_W_BYTES) && (m_tiles * n_tiles >= 2 * kSMs);
+  if (p.ws) {
+    const int grid = (kSMs / n_tiles) * n_tiles;
+    HFL_LAUNCH((k_gather_gemm<true><<<grid, G_THREADS, G_SMEM, st>>>(tmap, p)));
+  } else {
+    const int64_t tiles = m_tiles * n_tiles;
+    const int grid = (int)(tiles < kSMs ? tiles : kSMs);
+    HFL_LAUNCH((k_gather_gemm<false><<<grid, G_THREADS, G_SMEM, st>>>(tmap, p)));
+  }
   return HFL_OK;
 }
 

@@ -347,7 +347,7 @@ class _Engine:
             qs = []
             for ap in pool.attpool:
                 k, C = ap.query.shape
-                npad = (k + 31) // 32 * 32
+                npad = (k + 63) // 64 * 64
                 q = torch.zeros(npad, C, dtype=torch.bfloat16, device=ap.query.device)
                 q[:k] = ap.query.detach().to(torch.bfloat16)
                 qs.append((q, k, npad))
