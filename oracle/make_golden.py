@@ -150,5 +150,49 @@ def main():
     print('golden vectors written to', OUT)
 
 
+
+def recall_case(seed=11, n_runs=3, n_per_run=300, dim=256):
+    """Synthetic evaluation sets in the reference's pickle format
+    (datasets/WildPlaces/generate_test_sets.py:46-78): list over runs of
+    {idx: {'query': path, 'northing', 'easting', <db_run>: [true neighbour ids]}}."""
+    rng = np.random.default_rng(seed)
+    sets, vecs = [], []
+    base = rng.normal(size=(n_per_run, dim)).astype(np.float32)
+    for r in range(n_runs):
+        pos = np.stack([np.arange(n_per_run) * 10.0, np.zeros(n_per_run)], 1)
+        v = base + 2.0 * rng.normal(size=base.shape).astype(np.float32)
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        vecs.append(v.astype(np.float32))
+        sets.append({i: {'query': f'run{r}/{i}.bin', 'northing': float(pos[i, 0]),
+                         'easting': float(pos[i, 1])} for i in range(n_per_run)})
+    for r in range(n_runs):
+        for i in range(n_per_run):
+            for m in range(n_runs):
+                near = [j for j in range(n_per_run) if abs(j - i) <= 1] if (i % 7) else []
+                sets[r][i][m] = near
+    return sets, vecs
+
+
+def make_recall_golden():
+    """Reference get_recall (eval/pnv_evaluate.py:228-315, sklearn KDTree path) on
+    synthetic sets -> tests/golden/recall.npz."""
+    S.install()
+    import importlib
+    ev = importlib.import_module('eval.pnv_evaluate')
+    sets, vecs = recall_case()
+    out = {}
+    for m in range(3):
+        for n in range(3):
+            if m == n:
+                continue
+            rec, opr, mrr = ev.get_recall(m, n, vecs, vecs, sets, sets)
+            out[f'recall_{m}_{n}'] = np.asarray(rec)
+            out[f'opr_{m}_{n}'] = np.asarray(opr)
+            out[f'mrr_{m}_{n}'] = np.asarray(mrr)
+    np.savez_compressed(os.path.join(OUT, 'recall.npz'), **out)
+    print('recall golden written')
+
+
 if __name__ == '__main__':
     main()
+    make_recall_golden()

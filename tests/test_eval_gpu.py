@@ -1,0 +1,91 @@
+"""GPU tests of the evaluation entry points (eval/pnv_evaluate.py mirror): file loaders ->
+batched octree -> descriptors -> exact top-k -> recall, against the reference's get_recall
+golden and against the CPU oracle's descriptors on the same synthetic dataset."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as M
+from oracle import octree_ref as R
+from oracle.make_golden import recall_case
+from tests.common import GOLDEN, cosine
+
+pytestmark = pytest.mark.gpu
+
+
+def test_get_recall_matches_reference_golden():
+    from hotformerloc_b200.eval.pnv_evaluate import get_recall
+    sets, vecs = recall_case()
+    gold = np.load(os.path.join(GOLDEN, 'recall.npz'))
+    for m in range(3):
+        for n in range(3):
+            if m == n:
+                continue
+            rec, opr, mrr = get_recall(m, n, vecs, vecs, sets, sets)
+            # recall@N within 0.1 pt (BASELINE.json north_star); here exact
+            assert np.abs(rec - gold[f'recall_{m}_{n}']).max() < 0.1
+            assert abs(opr - gold[f'opr_{m}_{n}']) < 0.1 and abs(mrr - gold[f'mrr_{m}_{n}']) < 0.1
+
+
+def test_evaluate_end_to_end_vs_oracle(tmp_path):
+    """2 runs x 10 submaps written as .bin files + evaluation pickles; evaluate() through the
+    public entry point; descriptors and recall vs the fp32 CPU oracle."""
+    from hotformerloc_b200.config.presets import write_configs, TRAIN_PRESETS
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    from hotformerloc_b200.misc.utils import TrainingParams
+    from hotformerloc_b200.models.model_factory import model_factory
+    root = str(tmp_path)
+    g = torch.Generator().manual_seed(77)
+    n_sub, runs = 10, 2
+    base = [M.lidar_cloud(4096, g) for _ in range(n_sub)]
+    sets = []
+    for r in range(runs):
+        os.makedirs(os.path.join(root, f'run{r}'))
+        s = {}
+        for i in range(n_sub):
+            jitter = 0.002 * torch.randn(4096, 3, generator=g).numpy()
+            pts = np.clip(base[i] + jitter, -1, 1).astype(np.float64)
+            pts.tofile(os.path.join(root, f'run{r}', f'{i}.bin'))
+            s[i] = {'query': f'run{r}/{i}.bin', 'northing': float(i), 'easting': 0.0}
+            for m in range(runs):
+                s[i][m] = [i]
+        sets.append(s)
+    for name in ('oxford', 'university', 'residential', 'business'):
+        pickle.dump(sets, open(os.path.join(root, f'{name}_evaluation_database.pickle'), 'wb'))
+        pickle.dump(sets, open(os.path.join(root, f'{name}_evaluation_query.pickle'), 'wb'))
+    paths = write_configs(root, 'oxford', dataset_folder=root)
+    cfg = open(paths['config']).read().replace('val_batch_size=256', 'val_batch_size=4')
+    open(paths['config'], 'w').write(cfg)
+    params = TrainingParams(paths['config'], paths['model_config'])
+    assert params.val_batch_size == 4
+    torch.manual_seed(0)
+    model = model_factory(params.model_params).cuda().eval()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    emb = [E.get_latent_vectors(model, s, 'cuda', params) for s in sets]
+    # oracle descriptors with the reference's batch composition (chunks of val_batch_size)
+    hp = M.HParams.from_cfg(paths['model_config'])
+    ref = []
+    for r in range(runs):
+        out = []
+        for b in range(0, n_sub, 4):
+            clouds = [np.fromfile(os.path.join(root, f'run{r}', f'{i}.bin')).astype(np.float32).reshape(-1, 3)
+                      for i in range(b, min(b + 4, n_sub))]
+            out.append(M.forward(sd, R.build_batch(clouds, 9), hp).numpy())
+        ref.append(np.concatenate(out))
+    for r in range(runs):
+        assert cosine(emb[r], ref[r]).min() >= 0.999
+    rec, opr, mrr = E.get_recall(0, 1, emb, emb, sets, sets)
+    rec_o, opr_o, mrr_o = E.recall_from_neighbors(
+        np.argsort(((ref[1][:, None] - ref[0][None]) ** 2).sum(-1), axis=1)[:, :10], sets[1], 0, n_sub)
+    assert abs(rec[0] - rec_o[0]) < 0.1 and abs(opr - opr_o) < 0.1
+    rec_o2, _, _ = E.recall_from_neighbors(
+        np.argsort(((ref[0][:, None] - ref[1][None]) ** 2).sum(-1), axis=1)[:, :10], sets[0], 1, n_sub)
+    stats = E.evaluate(model, 'cuda', params)
+    assert set(stats) == {'oxford', 'university', 'residential', 'business', 'average'}
+    # evaluate() averages the (db 0, query 1) and (db 1, query 0) pairs (skip_same_run)
+    assert abs(stats['oxford']['ave_recall'][0] - 0.5 * (rec_o[0] + rec_o2[0])) < 0.1
+    E.pnv_write_eval_stats(os.path.join(root, 'res.txt'), 'prefix', stats)
+    assert 'AR@1' in open(os.path.join(root, 'res.txt')).read()

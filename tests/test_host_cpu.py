@@ -1,0 +1,174 @@
+"""CPU tests of the host-side logic: C-ABI surface, config schema, state_dict layout,
+loaders, evaluation bookkeeping, relay-token tables, and the multi-process sharding
+(gloo, world_size 2)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_ref as M
+from oracle import octree_ref as R
+from oracle.make_golden import CASES, recall_case
+from tests.common import GOLDEN, ROOT, case_clouds
+
+
+def test_library_exports_every_declared_symbol():
+    from hotformerloc_b200 import native
+    path = native.build()
+    header = open(os.path.join(ROOT, 'include', 'hfl.h')).read()
+    declared = set(re.findall(r'\b(hfl_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    import ctypes
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/hfl.h but not exported'
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    assert lib.hfl_version() >= 100
+    # the product path has no CPU fallback: building an octree without CUDA must fail loudly
+    if not torch.cuda.is_available():
+        from hotformerloc_b200.octree import build_batch
+        with pytest.raises(Exception):
+            build_batch([np.zeros((10, 3), np.float32)], 7, 2, 'cpu')
+
+
+@pytest.mark.parametrize('cfg', ['oxford', 'cs-wild-places', 'wild-places', 'cs-campus3d'])
+def test_config_schema_and_state_dict_layout(cfg, tmp_path):
+    from hotformerloc_b200.config.presets import write_configs
+    from hotformerloc_b200.misc.utils import TrainingParams
+    from hotformerloc_b200.models.model_factory import model_factory
+    paths = write_configs(str(tmp_path), cfg, dataset_folder=str(tmp_path))
+    params = TrainingParams(paths['config'], paths['model_config'])
+    assert params.load_octree and params.model_params.num_pyramid_levels == 3
+    model = model_factory(params.model_params)
+    ref = json.load(open(os.path.join(GOLDEN, f'state_shapes_{cfg}.json')))
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref                       # names AND shapes of the reference checkpoint layout
+    model.load_state_dict(M.synthetic_state_dict(ref))
+
+
+def test_loaders(tmp_path):
+    from hotformerloc_b200.datasets.pointnetvlad.pnv_raw import PNVPointCloudLoader
+    from hotformerloc_b200.datasets.CSWildPlaces.CSWildPlaces_raw import CSWildPlacesPointCloudLoader
+    pts = np.random.default_rng(0).uniform(-1, 1, (100, 3))
+    p = tmp_path / 'a.bin'
+    pts.astype(np.float64).tofile(p)
+    assert np.array_equal(PNVPointCloudLoader()(str(p)), pts.astype(np.float32))
+    hdr = ('# .PCD v0.7\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\n'
+           'COUNT 1 1 1 1\nWIDTH 100\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 100\n')
+    rec = np.concatenate([pts.astype(np.float32), np.ones((100, 1), np.float32)], 1)
+    with open(tmp_path / 'b.pcd', 'wb') as f:
+        f.write((hdr + 'DATA binary\n').encode())
+        f.write(rec.tobytes())
+    with open(tmp_path / 'c.pcd', 'w') as f:
+        f.write(hdr + 'DATA ascii\n')
+        for r in rec:
+            f.write(' '.join(repr(float(v)) for v in r) + '\n')
+    for name in ('b.pcd', 'c.pcd'):
+        assert np.array_equal(CSWildPlacesPointCloudLoader()(str(tmp_path / name)),
+                              pts.astype(np.float32))
+
+
+def test_cylindrical_matches_reference_golden():
+    from hotformerloc_b200.datasets.coordinate_utils import cylindrical_for_octree
+    g = np.load(os.path.join(GOLDEN, 'cylindrical.npz'))
+    assert np.array_equal(cylindrical_for_octree(g['cloud']), g['out'])
+
+
+def test_recall_bookkeeping_matches_reference_get_recall():
+    """tests/golden/recall.npz was produced by the reference's own get_recall."""
+    from hotformerloc_b200.eval.pnv_evaluate import recall_from_neighbors
+    sets, vecs = recall_case()
+    gold = np.load(os.path.join(GOLDEN, 'recall.npz'))
+    for m in range(3):
+        for n in range(3):
+            if m == n:
+                continue
+            d = ((vecs[n][:, None, :].astype(np.float64) - vecs[m][None]) ** 2).sum(-1)
+            idx = np.argsort(d, axis=1, kind='stable')[:, :25]
+            rec, opr, mrr = recall_from_neighbors(idx, sets[n], m, len(vecs[m]))
+            assert np.allclose(rec, gold[f'recall_{m}_{n}'])
+            assert np.isclose(opr, gold[f'opr_{m}_{n}']) and np.isclose(mrr, gold[f'mrr_{m}_{n}'])
+
+
+@pytest.mark.parametrize('name', ['cswp_b6_stress', 'oxford_b4_init'])
+def test_relay_token_tables_match_reference_octree_t(name):
+    """The engine's host tables vs the reference's OctreeT.build_t (tests/golden/octree_t.npz),
+    including submaps that own zero relay tokens at the coarsest level."""
+    from hotformerloc_b200.models.hotformerloc import _Engine
+    cfg, depth, spec, seed, mode = CASES[name]
+    gold = np.load(os.path.join(GOLDEN, 'octree_t.npz'))
+    K = 64 if cfg == 'cs-wild-places' else 48
+    ref = R.build_batch(case_clouds(name), depth, neigh=False)
+    B, d0 = ref.batch_size, depth - 2
+    depths = [d0 - 1 - j for j in range(3)]
+
+    class FakeOct:
+        device = 'cpu'
+        batch_nnum_nempty = torch.from_numpy(ref.batch_nnum_nempty)
+    nl = [int(ref.nnum_nempty[d]) for d in depths]
+    npad = [-(-v // (4 * K)) * 4 * K for v in nl]
+    nwin = [v // K for v in npad]
+    rows = [v * (K + 1) for v in nwin]
+    Roff = np.concatenate([[0], np.cumsum(rows)])
+    from hotformerloc_b200 import native
+    class _Pool:                                     # CPU stand-in for the pinned staging pool
+        def take(self, n): return torch.empty(n, dtype=torch.uint8)
+        def mark(self): pass
+    saved, native.pinned = native.pinned, _Pool()
+    try:
+        t = _Engine.__new__(_Engine)._host_tables(FakeOct, depths, nl, npad, nwin, Roff, K, B)
+    finally:
+        native.pinned = saved
+    for j, d in enumerate(depths):
+        assert npad[j] == int(gold[f'{name}_nnum_a_{d}'])
+        assert np.array_equal(t['num_windows'][j], gold[f'{name}_num_windows_{d}'])
+    tot = np.sum(t['num_windows'], 0)
+    assert np.array_equal(tot, gold[f'{name}_rt_combined'])
+    # attention-allowed pattern of the padded (B,N,N) reference mask vs the ragged ids
+    shp = tuple(gold[f'{name}_rt_attn_shape'])
+    allowed = np.unpackbits(gold[f'{name}_rt_attn_allowed'])[:np.prod(shp)].reshape(shp).astype(bool)
+    cu, ids = t['cu'].numpy(), t['ids'].numpy()
+    for b in range(B):
+        i = ids[cu[b]:cu[b + 1]]
+        assert np.array_equal(i[:, None] == i[None, :], allowed[b, :len(i), :len(i)])
+    # rt rows: level-major window order inside each submap, hat-layout row of each relay token
+    rt_rows = t['rt_rows'].numpy()
+    for b in range(B):
+        seg = rt_rows[cu[b]:cu[b + 1]]
+        o = 0
+        for j in range(3):
+            nw = int(t['num_windows'][j][b])
+            start = int(np.cumsum(t['num_windows'][j])[b] - nw)
+            assert np.array_equal(seg[o:o + nw], Roff[j] + (start + np.arange(nw)) * (K + 1))
+            o += nw
+
+
+def test_sharding_two_ranks_gloo(tmp_path):
+    """world_size-2 gloo run of the batch-granular sharding + descriptor gather."""
+    script = tmp_path / 'w.py'
+    script.write_text('''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from hotformerloc_b200.eval.pnv_evaluate import shard_batches, gather_rows
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+n, bs = 1037, 128
+spans = shard_batches(n, bs, rank, world)
+assert [t for t, _, _ in spans] == list(range(rank, (n + bs - 1) // bs, world))
+local = torch.cat([torch.arange(b, e, dtype=torch.float32)[:, None].repeat(1, 4) for _, b, e in spans])
+full = gather_rows(local, spans, n, rank, world)
+assert torch.equal(full, torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 4)), rank
+dist.destroy_process_group()
+print('ok', rank)
+''' % ROOT)
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29571')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                        '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port',
+                        '29571', str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count('ok') == 2
