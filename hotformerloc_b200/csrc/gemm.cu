@@ -31,15 +31,17 @@ constexpr int G_BK = 64;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;    // 16 KB
 constexpr int G_B_BYTES = 256 * G_BK * 2;     // 32 KB (block_n <= 256)
 constexpr int G_THREADS = 416;       // 8 epilogue + 1 MMA + 4 producer warps
+constexpr int G_PROD_THREADS = 128;
 constexpr int G_W_MMA = 8, G_W_PROD = 9;
 // streaming mode: 4 stages of (A 16 KB + B 32 KB); weight-stationary mode (Ktot*block_n*2 <=
 // 128 KB): the whole W tile lives in smem for the lifetime of the CTA and 4 stages of A stream.
-constexpr int G_STAGES_STREAM = 4, G_LAG_STREAM = 2;
-constexpr int G_STAGES_WS = 4, G_LAG_WS = 2;
+constexpr int G_STAGES_STREAM = 4;
+constexpr int G_STAGES_WS = 4;
 constexpr int G_WS_W_BYTES = 128 * 1024;
 constexpr int G_PIPE_BYTES = 192 * 1024;      // = 4*(16+32) KB (stream) = 4*16 KB + 128 KB (WS)
 constexpr int G_STAGE_BYTES = 8 * 2048;       // per epilogue warp: 32 rows x 64 B transpose buffer
-constexpr int G_SMEM = G_PIPE_BYTES + G_STAGE_BYTES + 256 + 2048 + 1024;   // + barriers + LN exchange + align
+constexpr int G_VEC_BYTES = 2 * 3 * 128 * 4;   // per column half: bias | gamma | beta
+constexpr int G_SMEM = G_PIPE_BYTES + G_STAGE_BYTES + 256 + 2048 + G_VEC_BYTES;   // + barriers + LN exchange
 
 struct GemmParams {
   const __nv_bfloat16* A;   // [rows_A, Cin]
@@ -178,11 +180,10 @@ template <bool WS>
 __global__ void __launch_bounds__(G_THREADS, 1)
 k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   constexpr int G_STAGES = WS ? G_STAGES_WS : G_STAGES_STREAM;
-  constexpr int G_LAG = WS ? G_LAG_WS : G_LAG_STREAM;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = ptx::smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = ptx::smem_u32(smem_raw);
+  if (base & 1023u) __trap();                           // SWIZZLE_128B operands need 1024 B alignment
+  uint8_t* smem = smem_raw;
   const uint32_t sA = base;
   const uint32_t sB = base + G_STAGES * G_A_BYTES;      // stream: B ring; WS: resident W tile
   const uint32_t sStage = base + G_PIPE_BYTES;          // epilogue transpose buffers
@@ -194,6 +195,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   const uint32_t bar_w = bar_tempty + 16;               // 8 B (WS: W tile landed)
   const uint32_t s_tmem = bar_w + 8;                    // 4 B
   float2* s_ln = reinterpret_cast<float2*>(smem + (sBar + 256 - base));   // [2 halves][128 rows]
+  float* s_vec = reinterpret_cast<float*>(smem + (sBar + 256 + 2048 - base));   // [2 halves][3][128]
   volatile uint32_t* tmem_ptr_s =
       reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - base));
 
@@ -210,7 +212,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, WS ? 128 : 128 + 1);
+      ptx::mbar_init(bar_full + 8 * s, WS ? G_PROD_THREADS : G_PROD_THREADS + 1);
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
     ptx::mbar_init(bar_w, 1);
@@ -233,6 +235,8 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     // ===================== A producers (+ TMA for W) =====================
     // 128 threads; thread = (16-byte chunk c of the 128-byte K-block row, rows rbase + 16 i):
     // 8 consecutive lanes fetch one full 128-byte line -> every cp.async is sector-complete.
+    constexpr int RPT = G_BM * 8 / G_PROD_THREADS;       // rows per thread = 8
+    constexpr int RSTEP = G_PROD_THREADS / 8;            // 16
     const int pt = (warp - G_W_PROD) * 32 + lane;
     const int c = pt & 7, rbase = pt >> 3;
     const bool tma_thread = (pt == 0);
@@ -253,10 +257,10 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
         const int kk = kglob / p.Cin;
         const int ch = kglob - kk * p.Cin;
         // gather rows for this K-block (issued before the slot wait to overlap its latency)
-        int64_t src_row[8];
+        int64_t src_row[RPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = m0 + 16 * i;
+        for (int i = 0; i < RPT; ++i) {
+          const int m = m0 + RSTEP * i;
           src_row[i] = m >= p.M ? -1 : (p.idx ? (int64_t)__ldg(p.idx + (size_t)m * p.KD + kk) : (int64_t)m);
         }
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -266,24 +270,18 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
         }
         const uint32_t dst = sA + s * G_A_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rbase + 16 * i;
+        for (int i = 0; i < RPT; ++i) {
+          const int r = rbase + RSTEP * i;
           const bool ok = src_row[i] >= 0;
           const __nv_bfloat16* src = p.A + (ok ? (size_t)src_row[i] * p.Cin + ch : 0);
           ptx::cp_async16(dst + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4), src, ok ? 16u : 0u);
         }
-        ptx::cp_async_commit();
-        if (g >= G_LAG) {
-          ptx::cp_async_wait<G_LAG>();
-          ptx::fence_proxy_async();
-          ptx::mbar_arrive(bar_full + 8 * ((g - G_LAG) % G_STAGES));
-        }
+        // asynchronous arrive: fires when this thread's copies have landed, so the producer never
+        // blocks on data and every free stage of the ring is in flight
+        ptx::cp_async_mbar_arrive_noinc(bar_full + 8 * s);
       }
     }
-    ptx::cp_async_wait<0>();
-    ptx::fence_proxy_async();
-    const uint32_t first = g >= G_LAG ? g - G_LAG : 0;
-    for (uint32_t q = first; q < g; ++q) ptx::mbar_arrive(bar_full + 8 * (q % G_STAGES));
+    ptx::cp_async_wait<0>();                             // do not exit with copies in flight
   } else if (warp == G_W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -301,6 +299,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
         for (int kb = 0; kb < k_blocks; ++kb, ++g) {
           const uint32_t s = g % G_STAGES, ph = (g / G_STAGES) & 1;
           ptx::mbar_wait(bar_full + 8 * s, ph);
+          ptx::fence_proxy_async();                      // cp.async (generic proxy) -> UMMA (async proxy)
           ptx::tc_fence_after();
           const uint64_t ad = ptx::umma_desc_sw128(sA + s * G_A_BYTES);
           const uint64_t bd = ptx::umma_desc_sw128(WS ? sB + kb * (BN * G_BK * 2) : sB + s * G_B_BYTES);
@@ -321,56 +320,73 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     const int HB = BN >> 1;                              // columns per half (multiple of 32)
     const int cbeg = half * HB;
     const uint32_t stage = sStage + (uint32_t)warp * 2048u;
+    float* v_bias = s_vec + half * 384;                  // this half's columns: bias | gamma | beta
+    float* v_g = v_bias + 128;
+    float* v_b = v_bias + 256;
+    const bool do_ln = p.ln_g != nullptr;
+    const bool has_res = p.res != nullptr;
+    int loaded_n0 = -1;
     uint32_t it = 0;
     for (int t = t_begin; t < t_end; t += t_step, ++it) {
       const int m_blk = WS ? t : t / p.n_tiles, n_blk = WS ? ws_n_blk : t % p.n_tiles;
       const uint32_t acc = it & 1, aph = (it >> 1) & 1;
       const int m = m_blk * G_BM + r;
       const int n0 = n_blk * BN;
+      if (n0 != loaded_n0) {                             // epilogue vectors -> smem (once per CTA in WS mode)
+        asm volatile("bar.sync %0, 128;" ::"r"(5 + half) : "memory");   // previous tile's readers done
+        if (r < HB) {
+          v_bias[r] = p.bias ? __ldg(p.bias + n0 + cbeg + r) : 0.f;
+          if (do_ln) { v_g[r] = __ldg(p.ln_g + cbeg + r); v_b[r] = __ldg(p.ln_b + cbeg + r); }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(5 + half) : "memory");
+        loaded_n0 = n0;
+      }
       int32_t orow = -1;
       if (m < p.M) orow = p.out_rows ? __ldg(p.out_rows + m) : m;
       const int32_t yrow = p.y_mapped ? orow : (m < p.M ? m : -1);
-      const bool do_ln = p.ln_g != nullptr;
-      const bool has_res = p.res != nullptr;
       uint4 rbuf[8];
       if (has_res) res_issue(p.res, orow, p.N, n0 + cbeg, lane, rbuf);   // first residual chunk
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + cbeg;
       float shift = 0.f, s1 = 0.f, s2 = 0.f;              // shifted sums for LayerNorm
+      uint32_t rawA[32];
       for (int c0 = 0; c0 < HB; c0 += 32) {
-        uint32_t raw32[32];
-        ptx::tmem_ld32(taddr + c0, raw32);
-        ptx::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw32[j]);
-        if (p.bias) {
+        {
+          const int cc = c0;
+          uint32_t (&raw32)[32] = rawA;
+          ptx::tmem_ld32(taddr + cc, raw32);
+          ptx::tmem_ld_wait();
+          float v[32];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cbeg + c0) + q);
-            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            const float4 b = *reinterpret_cast<const float4*>(v_bias + cc + 4 * q);
+            v[4 * q] = __uint_as_float(raw32[4 * q]) + b.x;
+            v[4 * q + 1] = __uint_as_float(raw32[4 * q + 1]) + b.y;
+            v[4 * q + 2] = __uint_as_float(raw32[4 * q + 2]) + b.z;
+            v[4 * q + 3] = __uint_as_float(raw32[4 * q + 3]) + b.w;
           }
-        }
-        if (has_res) {
-          res_add(stage, lane, rbuf, v);
-          if (c0 + 32 < HB) res_issue(p.res, orow, p.N, n0 + cbeg + c0 + 32, lane, rbuf);
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (p.out_v_f32) store_f32x32(stage, lane, p.out_v_f32, orow, p.N, n0 + cbeg + c0, v);
-        if (p.out_v_bf16) store_bf16x32(stage, lane, p.out_v_bf16, orow, p.N, n0 + cbeg + c0, v);
-        if (do_ln) {
-          if (c0 == 0) shift = v[0];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = v[j] - shift;
-            s1 += d; s2 += d * d;
-            raw32[j] = __float_as_uint(v[j]);
+          if (has_res) {
+            res_add(stage, lane, rbuf, v);
+            if (cc + 32 < HB) res_issue(p.res, orow, p.N, n0 + cbeg + cc + 32, lane, rbuf);
           }
-          ptx::tmem_st32(taddr + c0, raw32);
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (p.out_v_f32) store_f32x32(stage, lane, p.out_v_f32, orow, p.N, n0 + cbeg + cc, v);
+          if (p.out_v_bf16) store_bf16x32(stage, lane, p.out_v_bf16, orow, p.N, n0 + cbeg + cc, v);
+          if (do_ln) {
+            if (cc == 0) shift = v[0];
+            uint32_t wb[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = v[j] - shift;
+              s1 += d; s2 += d * d;
+              wb[j] = __float_as_uint(v[j]);
+            }
+            ptx::tmem_st32(taddr + cc, wb);
+          }
         }
       }
       if (do_ln) {
@@ -387,25 +403,28 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
         const float var = (m2_h + o.y + delta * delta * nh * 0.5f) / (2.f * nh);
         const float rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
         for (int c0 = 0; c0 < HB; c0 += 32) {
-          uint32_t raw32[32];
-          ptx::tmem_ld32(taddr + c0, raw32);
-          ptx::tmem_ld_wait();
-          float y[32];
+          {
+            const int cc = c0;
+            uint32_t (&raw32)[32] = rawA;
+            ptx::tmem_ld32(taddr + cc, raw32);
+            ptx::tmem_ld_wait();
+            float y[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 gm = __ldg(reinterpret_cast<const float4*>(p.ln_g + cbeg + c0) + q);
-            float4 bt = __ldg(reinterpret_cast<const float4*>(p.ln_b + cbeg + c0) + q);
-            y[4 * q] = (__uint_as_float(raw32[4 * q]) - mean) * rstd * gm.x + bt.x;
-            y[4 * q + 1] = (__uint_as_float(raw32[4 * q + 1]) - mean) * rstd * gm.y + bt.y;
-            y[4 * q + 2] = (__uint_as_float(raw32[4 * q + 2]) - mean) * rstd * gm.z + bt.z;
-            y[4 * q + 3] = (__uint_as_float(raw32[4 * q + 3]) - mean) * rstd * gm.w + bt.w;
-          }
-          if (p.relu) {
+            for (int q = 0; q < 8; ++q) {
+              const float4 gm = *reinterpret_cast<const float4*>(v_g + cc + 4 * q);
+              const float4 bt = *reinterpret_cast<const float4*>(v_b + cc + 4 * q);
+              y[4 * q] = (__uint_as_float(raw32[4 * q]) - mean) * rstd * gm.x + bt.x;
+              y[4 * q + 1] = (__uint_as_float(raw32[4 * q + 1]) - mean) * rstd * gm.y + bt.y;
+              y[4 * q + 2] = (__uint_as_float(raw32[4 * q + 2]) - mean) * rstd * gm.z + bt.z;
+              y[4 * q + 3] = (__uint_as_float(raw32[4 * q + 3]) - mean) * rstd * gm.w + bt.w;
+            }
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+              for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+            }
+            if (p.out_y_f32) store_f32x32(stage, lane, p.out_y_f32, yrow, p.N, cbeg + cc, y);
+            if (p.out_y_bf16) store_bf16x32(stage, lane, p.out_y_bf16, yrow, p.N, cbeg + cc, y);
           }
-          if (p.out_y_f32) store_f32x32(stage, lane, p.out_y_f32, yrow, p.N, cbeg + c0, y);
-          if (p.out_y_bf16) store_bf16x32(stage, lane, p.out_y_bf16, yrow, p.N, cbeg + c0, y);
         }
         // the exchange slot is rewritten only after both halves passed the next bar.sync
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");

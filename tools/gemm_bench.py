@@ -47,6 +47,8 @@ M1 = 1_050_000   # hat rows level 0 (B=256)
 bench('qkv C256', M1, 768, 256)
 bench('proj C256 +res+ln', M1, 256, 256, res=True, ln=True, bf16out=False)
 bench('proj C256 plain', M1, 256, 256)
+bench('proj C256 +res f32out', M1, 256, 256, res=True, bf16out=False)
+bench('proj C256 +ln bf16 only', M1, 256, 256, ln=True, bf16out=False)
 bench('fc1 C256 gelu', M1, 1024, 256, act=True)
 bench('fc1 C256 nogelu', M1, 1024, 256)
 bench('fc2 C256 +res', M1, 256, 1024, res=True)
@@ -61,3 +63,23 @@ bench('conv 27x64->64', 1_047_000, 64, 1728, KD=27, ln=True, bf16out=False)
 bench('down 8x128->256', 955_000, 256, 1024, KD=8, ln=True, bf16out=False)
 bench('down 8x256->256', 706_000, 256, 2048, KD=8, ln=True, bf16out=False)
 bench('small M qkv', 43_000, 768, 256)
+
+# --- epilogue decomposition experiments (QKV shape) ---
+def raw(name, M, N, K, **args):
+    A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(torch.bfloat16)
+    f = lambda: ops.gather_gemm(A, W, **args)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10): f()
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f'{name:28s} {ms:8.3f} ms  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s')
+
+raw('qkv: no outputs at all', M1, 768, 256)
+raw('qkv: bf16 out, no bias', M1, 768, 256, out_v_bf16=torch.empty(M1, 768, device=dev, dtype=torch.bfloat16))
+raw('qkv: f32 out, no bias', M1, 768, 256, out_v_f32=torch.empty(M1, 768, device=dev))
+raw('N=256 K=256 no outputs', M1, 256, 256)
+raw('N=256 K=1024 no outputs', M1, 256, 1024)
