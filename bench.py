@@ -299,8 +299,9 @@ def run_reference(args, rank, world):
            'n_gpus': world, 'steps': args.steps, 'warmup': min(args.warmup, 1),
            'ms_per_step': cpu['seconds_per_step'] * 1e3, 'higher_is_better': True,
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': f'{args.config} cfg, {args.points}-point synthetic submaps, '
-                                  f'{sample} submaps per step (bounded sample of the 256-submap batch)'},
+           'config': {'workload': f'{args.config} cfg, {args.batch} synthetic {args.points}-point submaps per step per GPU, '
+                                  f'random-init weights (BASELINE.json configs[1])',
+                      'sample': f'each step = {sample} submaps of that workload on the host cores'},
            'cpu_baseline': cpu,
            'e2e': {'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
                    'd2h_bytes_per_step': 0}}
