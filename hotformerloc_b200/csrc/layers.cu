@@ -12,6 +12,7 @@
 // "hat" layout (hierarchical attention): K window tokens preceded by their relay token,
 //   row(token t) = t + t / K + 1,  row(RT of window w) = w * (K + 1).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace hfl {
 
@@ -127,7 +128,7 @@ struct CpeParams {
   float* x;                    // [rows, C] fp32 residual stream (updated in place)
   const __nv_bfloat16* xb;     // [rows, C] bf16 shadow (gather source, not modified)
   const int32_t* ne;           // [n, 27] neighbour table, token index space
-  const float* w;              // [27, C] depth-wise weights
+  const __nv_bfloat16* w;      // [27, C] depth-wise weights (bf16: one 16 B load per lane and tap)
   const float *g_cpe, *b_cpe;  // CPE LayerNorm
   const float *g1, *b1;        // block norm1 (NULL: skip)
   __nv_bfloat16* y1;           // [rows, C] LN1(x) bf16 (NULL: skip)
@@ -157,16 +158,17 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
       float acc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) acc[j] = 0.f;
-#pragma unroll 1
-      for (int k = 0; k < 27; ++k) {
+      // visit only the occupied neighbours (about a third of the 27 taps on lidar surfaces)
+      unsigned todo = __ballot_sync(0xffffffffu, my >= 0);
+      while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
         const int32_t ni = __shfl_sync(0xffffffffu, my, k);
-        if (ni >= 0) {
-          float nv[V], wv[V];
-          load_bf16<V>(p.xb + hat_row(ni, p.K) * C + c0, nv);
-          load_f32<V>(p.w + k * C + c0, wv);
+        float nv[V], wv[V];
+        load_bf16<V>(p.xb + hat_row(ni, p.K) * C + c0, nv);
+        load_bf16<V>(p.w + k * C + c0, wv);
 #pragma unroll
-          for (int j = 0; j < V; ++j) acc[j] += wv[j] * nv[j];
-        }
+        for (int j = 0; j < V; ++j) acc[j] = fmaf(wv[j], nv[j], acc[j]);
       }
       warp_ln<V>(acc, p.g_cpe, p.b_cpe, c0, 1e-5f);
       if (p.cpe_out) {
@@ -331,7 +333,8 @@ __global__ void k_f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __res
 // ---------------------------------------------------------------------------
 struct PoolParams {
   const float* logits;   // [rows, ldl]
-  const float* x;        // [rows, C] fp32 features, hat layout
+  const float* x;        // [rows, C] fp32 features, hat layout (unused by the MMA path)
+  const __nv_bfloat16* xb; // [rows, C] bf16 shadow of the features
   const int32_t* tok_off; // [B+1] token offsets of the submaps at this level
   float* stat;           // [B, kq, 2] (max, 1/sum) in log2 domain
   float* out;            // [B, ktot, C]; this level's queries start at q_off
@@ -360,42 +363,118 @@ __global__ void __launch_bounds__(256) k_pool_stats(const PoolParams p) {
   }
 }
 
-constexpr int PQ = 16;   // queries per CTA
-__global__ void __launch_bounds__(256) k_pool_sum(const PoolParams p) {
-  // grid: (B, ceil(kq/PQ)); thread = channel (C == blockDim.x)
-  __shared__ float sp[64][PQ];
-  __shared__ float sm[PQ], si[PQ];
-  const int b = blockIdx.x, q0 = blockIdx.y * PQ, c = threadIdx.x;
-  const int nq = min(PQ, p.kq - q0);
+// pass 2 on the tensor cores: out[q, c] = sum_t P[t, q] * x[t, c] is a (queries x tokens) x
+// (tokens x channels) product.  CTA = (submap, group of <= 80 queries); 8 warps x 32 channels;
+// per 64-token tile the CTA builds P (bf16, already normalised) in smem and streams the bf16
+// feature rows through a cp.async double buffer; mma.sync m16n8k16, fp32 accumulators.
+constexpr int PM_Q = 80;                  // queries per CTA (5 m-tiles)
+constexpr int PM_T = 64;                  // tokens per tile
+constexpr int PM_PP = 72;                 // sP pitch (bf16): 144 B rows, conflict-free ldmatrix
+constexpr int PM_XP = 264;                // sX pitch (bf16): 528 B rows
+constexpr int PM_SMEM = PM_Q * PM_PP * 2 + 2 * PM_T * PM_XP * 2 + PM_Q * 8 + PM_T * 8;
+
+__global__ void __launch_bounds__(256) k_pool_mma(const PoolParams p) {
+  extern __shared__ __align__(16) uint8_t psm[];
+  __nv_bfloat16* sP = reinterpret_cast<__nv_bfloat16*>(psm);                         // [80][72]
+  __nv_bfloat16* sX = reinterpret_cast<__nv_bfloat16*>(psm + PM_Q * PM_PP * 2);      // [2][64][264]
+  float* sM = reinterpret_cast<float*>(psm + PM_Q * PM_PP * 2 + 2 * PM_T * PM_XP * 2);
+  float* sI = sM + PM_Q;
+  int64_t* sRow = reinterpret_cast<int64_t*>(sI + PM_Q);                              // [64]
+  const int b = blockIdx.x, qbase = blockIdx.y * PM_Q;
+  const int nq = min(PM_Q, p.kq - qbase);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
   const int64_t t0 = p.tok_off[b], t1 = p.tok_off[b + 1];
   const float sc = p.scale * 1.4426950408889634f;
-  if (threadIdx.x < PQ) {
-    const bool ok = (int)threadIdx.x < nq;
-    sm[threadIdx.x] = ok ? p.stat[((size_t)b * p.kq + q0 + threadIdx.x) * 2] : 0.f;
-    si[threadIdx.x] = ok ? p.stat[((size_t)b * p.kq + q0 + threadIdx.x) * 2 + 1] : 0.f;
+  for (int q = threadIdx.x; q < PM_Q; q += 256) {
+    const bool ok = q < nq;
+    sM[q] = ok ? p.stat[((size_t)b * p.kq + qbase + q) * 2] : 0.f;
+    sI[q] = ok ? p.stat[((size_t)b * p.kq + qbase + q) * 2 + 1] : 0.f;
   }
-  float acc[PQ];
+  float acc[5][4][4];
 #pragma unroll
-  for (int j = 0; j < PQ; ++j) acc[j] = 0.f;
-  for (int64_t tb = t0; tb < t1; tb += 64) {
+  for (int m = 0; m < 5; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.f;
+  const uint32_t sX_u = ptx::smem_u32(sX), sP_u = ptx::smem_u32(sP);
+  const int n_tiles = (int)((t1 - t0 + PM_T - 1) / PM_T);
+
+  auto stage_x = [&](int tile, int buf) {
+    // 64 rows x 512 B = 2048 x 16 B chunks, 8 per thread; rows beyond the submap are zero-filled
+    const int64_t tb = t0 + (int64_t)tile * PM_T;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = threadIdx.x + 256 * i;
+      const int tt = ch >> 5, c16 = ch & 31;
+      const bool ok = tb + tt < t1;
+      const int64_t row = ok ? hat_row(tb + tt, p.K) : 0;
+      ptx::cp_async16(sX_u + (uint32_t)((buf * PM_T + tt) * PM_XP * 2 + c16 * 16),
+                      p.xb + row * p.C + c16 * 8, ok ? 16u : 0u);
+    }
+    ptx::cp_async_commit();
+  };
+  if (n_tiles > 0) stage_x(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int buf = tile & 1;
+    const int64_t tb = t0 + (int64_t)tile * PM_T;
+    __syncthreads();                                   // previous tile's sP / sX[buf^1] readers done
+    if (tile + 1 < n_tiles) stage_x(tile + 1, buf ^ 1);
+    if (threadIdx.x < PM_T) sRow[threadIdx.x] = tb + threadIdx.x < t1 ? hat_row(tb + threadIdx.x, p.K) : -1;
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * PQ; i += blockDim.x) {
-      const int tt = i / PQ, j = i % PQ;
+    // ---- P tile (normalised softmax weights), bf16, [query][token] ----
+    for (int i = threadIdx.x; i < PM_T * PM_Q; i += 256) {
+      const int tt = i / PM_Q, q = i - tt * PM_Q;
+      const int64_t row = sRow[tt];
       float pv = 0.f;
-      if (tb + tt < t1 && j < nq)
-        pv = exp2f(p.logits[hat_row(tb + tt, p.K) * p.ldl + q0 + j] * sc - sm[j]) * si[j];
-      sp[tt][j] = pv;
+      if (row >= 0 && q < nq)
+        pv = exp2f(p.logits[row * p.ldl + qbase + q] * sc - sM[q]) * sI[q];
+      sP[q * PM_PP + tt] = __float2bfloat16(pv);
     }
+    if (tile + 1 < n_tiles) ptx::cp_async_wait<1>(); else ptx::cp_async_wait<0>();
     __syncthreads();
-    const int lim = (int)min((int64_t)64, t1 - tb);
-    for (int tt = 0; tt < lim; ++tt) {
-      const float xv = p.x[hat_row(tb + tt, p.K) * p.C + c];
+    // ---- acc += P^T-tile x X-tile ----
 #pragma unroll
-      for (int j = 0; j < PQ; ++j) acc[j] += sp[tt][j] * xv;
+    for (int ks = 0; ks < PM_T / 16; ++ks) {
+      uint32_t bfr[2][4];
+      const int mi = lane >> 3;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int trow = ks * 16 + (mi & 1) * 8 + (lane & 7);
+        const int col = warp * 32 + h2 * 16 + (mi >> 1) * 8;
+        ptx::ldmatrix_x4_trans(bfr[h2], sX_u + (uint32_t)(((buf * PM_T + trow) * PM_XP + col) * 2));
+      }
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        uint32_t afr[4];
+        const int arow = m * 16 + (mi & 1) * 8 + (lane & 7);
+        const int acol = ks * 16 + (mi >> 1) * 8;
+        ptx::ldmatrix_x4(afr, sP_u + (uint32_t)((arow * PM_PP + acol) * 2));
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          uint32_t bb[2] = {bfr[n >> 1][(n & 1) * 2], bfr[n >> 1][(n & 1) * 2 + 1]};
+          ptx::mma16816(acc[m][n], afr, bb);
+        }
+      }
     }
   }
-  for (int j = 0; j < nq; ++j)
-    p.out[((size_t)b * p.ktot + p.q_off + q0 + j) * p.C + c] = acc[j];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int c = warp * 32 + n * 8 + 2 * t4;
+      const int q0 = m * 16 + g, q1 = q0 + 8;
+      if (q0 < nq) {
+        float* o = p.out + ((size_t)b * p.ktot + p.q_off + qbase + q0) * p.C + c;
+        o[0] = acc[m][n][0]; o[1] = acc[m][n][1];
+      }
+      if (q1 < nq) {
+        float* o = p.out + ((size_t)b * p.ktot + p.q_off + qbase + q1) * p.C + c;
+        o[0] = acc[m][n][2]; o[1] = acc[m][n][3];
+      }
+    }
+  }
 }
 
 // Mixer tail (salsa.py:103-111) + F.normalize (hotformerloc.py:55-56); one CTA per submap
@@ -472,7 +551,7 @@ int hfl_stem_conv(const float* leaf_pts, const int32_t* ne, int64_t n, int32_t d
   return HFL_OK;
 }
 
-int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const float* w, const float* g_cpe,
+int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const void* w, const float* g_cpe,
                const float* b_cpe, const float* g1, const float* b1, void* y1, float* cpe_out,
                int64_t n, int64_t rows, int32_t C, int32_t K, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
@@ -480,7 +559,7 @@ int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const float* w, cons
   HFL_CHECK_ARG(x && xb && ne && w && g_cpe && b_cpe, "null argument");
   HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
   HFL_CHECK_ARG(!y1 || (g1 && b1), "norm1 parameters missing");
-  CpeParams p{x, (const __nv_bfloat16*)xb, ne, w, g_cpe, b_cpe, g1, b1, (__nv_bfloat16*)y1, cpe_out, n, rows, K};
+  CpeParams p{x, (const __nv_bfloat16*)xb, ne, (const __nv_bfloat16*)w, g_cpe, b_cpe, g1, b1, (__nv_bfloat16*)y1, cpe_out, n, rows, K};
   if (C == 128) HFL_LAUNCH((k_cpe_ln<4><<<ROWS_GRID(rows), 256, 0, st>>>(p)));
   else HFL_LAUNCH((k_cpe_ln<8><<<ROWS_GRID(rows), 256, 0, st>>>(p)));
   return HFL_OK;
@@ -527,15 +606,20 @@ int hfl_f32_to_bf16(const float* in, void* out, int64_t n, void* stream_) {
   return HFL_OK;
 }
 
-int hfl_attn_pool(const float* logits, const float* x, const int32_t* tok_off, float* stat,
-                  float* out, int32_t B, int32_t kq, int32_t ldl, int32_t K, int32_t C,
+int hfl_attn_pool(const float* logits, const float* x, const void* xb, const int32_t* tok_off,
+                  float* stat, float* out, int32_t B, int32_t kq, int32_t ldl, int32_t K, int32_t C,
                   int32_t ktot, int32_t q_off, float scale, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  HFL_CHECK_ARG(logits && x && tok_off && stat && out, "null argument");
-  HFL_CHECK_ARG(C == 256 || C == 128, "C must equal the CTA size (128/256)");
-  PoolParams p{logits, x, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale};
+  HFL_CHECK_ARG(logits && xb && tok_off && stat && out, "null argument");
+  HFL_CHECK_ARG(C == 256, "C must be 256");
+  PoolParams p{logits, x, (const __nv_bfloat16*)xb, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale};
   HFL_LAUNCH((k_pool_stats<<<dim3(B, (kq + 7) / 8), 256, 0, st>>>(p)));
-  HFL_LAUNCH((k_pool_sum<<<dim3(B, (kq + PQ - 1) / PQ), C, 0, st>>>(p)));
+  static bool attr = false;
+  if (!attr) {
+    HFL_CUDA(cudaFuncSetAttribute(k_pool_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM));
+    attr = true;
+  }
+  HFL_LAUNCH((k_pool_mma<<<dim3(B, (kq + PM_Q - 1) / PM_Q), 256, PM_SMEM, st>>>(p)));
   return HFL_OK;
 }
 

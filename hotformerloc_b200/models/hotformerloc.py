@@ -315,7 +315,7 @@ class _Engine:
             else:
                 d['rpe'], d['bnd'] = None, 0
             if hasattr(b, 'cpe'):
-                d['cpe'] = (_f(b.cpe.conv.weights[:, 0, :]), _f(b.cpe.norm.weight),
+                d['cpe'] = (_bf(b.cpe.conv.weights[:, 0, :]), _f(b.cpe.norm.weight),
                             _f(b.cpe.norm.bias))
                 d['dil'] = b.dilation
             return d
@@ -341,7 +341,7 @@ class _Engine:
                               b2=_f(a.fc2.bias), mode=a.fc1.weight.shape[1])
         else:
             c = hs.relay_tokeniser.cpe
-            w['rt_cpe'] = (_f(c.conv.weights[:, 0, :]), _f(c.norm.weight), _f(c.norm.bias))
+            w['rt_cpe'] = (_bf(c.conv.weights[:, 0, :]), _f(c.norm.weight), _f(c.norm.bias))
         pool = self.m.pooling.pooling
         if isinstance(pool, PyramidAttnPoolWrapper):
             qs = []
@@ -521,7 +521,7 @@ class _Engine:
                 logits = E(rows[j], npd, dt=f32)
                 ops.gather_gemm(Xbl[j], q, out_v_f32=logits)
                 stat = E(B, k, 2, dt=f32)
-                ops.attn_pool(logits, Xl[j], tabs['tok_off'][j], stat, Tk, B, k, npd, K, C1, ktot,
+                ops.attn_pool(logits, Xl[j], Xbl[j], tabs['tok_off'][j], stat, Tk, B, k, npd, K, C1, ktot,
                               qoff, C1 ** -0.5)
                 qoff += k
             T2 = Tk.view(B * ktot, C1)

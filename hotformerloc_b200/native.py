@@ -107,7 +107,7 @@ SIGNATURES = {
     'hfl_hat_rows': (C.c_int, [_p, _i64, _i32, _i32, _p]),
     'hfl_remap_hat': (C.c_int, [_p, _p, _i64, _i32, _p]),
     'hfl_f32_to_bf16': (C.c_int, [_p, _p, _i64, _p]),
-    'hfl_attn_pool': (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
+    'hfl_attn_pool': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
     'hfl_mixer_tail': (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     'hfl_gem_pool': (C.c_int, [_p, _p, _i32, _i32, _i32, _f32, _f32, _p, _i32, _i32, _p]),
     'hfl_knn_topk': (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),

@@ -75,8 +75,8 @@ def f32_to_bf16(src, out):
     N.check(N.lib().hfl_f32_to_bf16(_p(src), _p(out), src.numel(), _s()))
 
 
-def attn_pool(logits, x, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale):
-    N.check(N.lib().hfl_attn_pool(_p(logits), _p(x), _p(tok_off), _p(stat), _p(out), B, kq, ldl, K,
+def attn_pool(logits, x, xb, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale):
+    N.check(N.lib().hfl_attn_pool(_p(logits), _p(x), _p(xb), _p(tok_off), _p(stat), _p(out), B, kq, ldl, K,
                                   C, ktot, q_off, float(scale), _s()))
 
 

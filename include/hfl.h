@@ -138,7 +138,7 @@ int hfl_stem_conv(const float* leaf_pts, const int32_t* ne, int64_t n, int32_t d
  * Replaces dwconv.core.dwconv_forward_backward (libs/dwconv/csrc/dwconv.cu:99-113,
  * pybind.cpp:10-14) + CPE norm (octformer_layers.py:138-142) + norm1.
  * K = 0: plain layout, else hat layout.  cpe_out != NULL: only LN(dwconv(x)) -> [n,C]. */
-int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const float* w, const float* g_cpe,
+int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const void* w_bf16, const float* g_cpe,
                const float* b_cpe, const float* g1, const float* b1, void* y1_bf16, float* cpe_out,
                int64_t n, int64_t rows, int32_t C, int32_t K, void* stream);
 
@@ -157,8 +157,8 @@ int hfl_remap_hat(const int32_t* in, int32_t* out, int64_t n, int32_t K, void* s
 int hfl_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* AdaptivePooling (salsa.py:25-55) given logits = x . query^T from hfl_gather_gemm. */
-int hfl_attn_pool(const float* logits, const float* x, const int32_t* tok_off, float* stat,
-                  float* out, int32_t B, int32_t kq, int32_t ldl, int32_t K, int32_t C,
+int hfl_attn_pool(const float* logits, const float* x, const void* x_bf16, const int32_t* tok_off,
+                  float* stat, float* out, int32_t B, int32_t kq, int32_t ldl, int32_t K, int32_t C,
                   int32_t ktot, int32_t q_off, float scale, void* stream);
 
 /* Mixer channel_proj + row_proj + flatten (salsa.py:105-111) + F.normalize (hotformerloc.py:55). */

@@ -187,12 +187,12 @@ def test_cpe_ln(C, K):
         x[::K + 1] = torch.randn(rows // (K + 1), C)
     ne = torch.randint(-1, n, (n, 27), dtype=torch.int32)
     ne[torch.rand(n, 27) < 0.6] = -1
-    w = torch.randn(27, C) / 5
+    w = (torch.randn(27, C) / 5).to(torch.bfloat16).float()
     g_c, b_c, g1, b1 = (torch.randn(C) for _ in range(4))
     xd = x.to(DEV)
     xb = _bf(xd)
     y1 = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
-    _ops().cpe_ln(xd, xb, ne.to(DEV), w.to(DEV), g_c.to(DEV), b_c.to(DEV), g1.to(DEV), b1.to(DEV),
+    _ops().cpe_ln(xd, xb, ne.to(DEV), _bf(w.to(DEV)), g_c.to(DEV), b_c.to(DEV), g1.to(DEV), b1.to(DEV),
                   y1, None, n, rows, C, K)
     src = xb.float().cpu()[tok_row[:n]]
     buf = src[ne.clamp(min=0).long()] * (ne >= 0).unsqueeze(-1)
@@ -208,7 +208,7 @@ def test_cpe_ln(C, K):
     assert torch.allclose(y1.float().cpu()[live], ref_y[live], atol=6e-2, rtol=2e-2)
     # cpe-only mode
     out = torch.zeros(n, C, device=DEV)
-    _ops().cpe_ln(xd, xb, ne.to(DEV), w.to(DEV), g_c.to(DEV), b_c.to(DEV), None, None, None, out,
+    _ops().cpe_ln(xd, xb, ne.to(DEV), _bf(w.to(DEV)), g_c.to(DEV), b_c.to(DEV), None, None, None, out,
                   n, rows, C, K)
     assert torch.allclose(out.cpu(), F.layer_norm(dw, (C,), g_c, b_c, 1e-5), atol=2e-4, rtol=1e-4)
 
