@@ -70,18 +70,19 @@ struct GemmParams {
 // division + exp of the textbook forms matter).  |GELU error| <= 2e-6 over [-8, 8]
 // (checked against scipy.special.erf), i.e. < 6 % of one bf16 ulp of the stored activation.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float a = x * 0.70710678118654752f;
-  const float t = fabsf(a), s = a * a;
-  float r = fmaf(-1.72853470e-5f, t, 3.83197126e-4f);
-  const float u = fmaf(-3.88396438e-3f, t, 2.42546219e-2f);
-  r = fmaf(r, s, u);
-  r = fmaf(r, t, -1.06777877e-1f);
-  r = fmaf(r, t, -6.34846687e-1f);
-  r = fmaf(r, t, -1.28717512e-1f);
-  r = fmaf(r, t, -t);
+  // constants of the erf polynomial with x/sqrt(2), log2(e) and the "-t" term folded in:
+  // GELU(x) = 0.5 (x + t) - 0.5 t * 2^(t P(t)),  t = |x|
+  const float t = fabsf(x), s = x * x;
+  float r = fmaf(-4.40836608e-6f, t, 1.38209148e-4f);
+  const float u = fmaf(-9.90546318e-4f, t, 8.74800568e-3f);
+  r = fmaf(r, s * 0.5f, u);
+  r = fmaf(r, t, -5.44641622e-2f);
+  r = fmaf(r, t, -4.57945084e-1f);
+  r = fmaf(r, t, -1.15144926f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * 1.4426950408889634f));
-  return 0.5f * x * (1.0f + copysignf(1.0f - e, x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * t));
+  const float ht = 0.5f * t;
+  return fmaf(-ht, e, fmaf(0.5f, x, ht));
 }
 
 // ---- coalesced epilogue I/O --------------------------------------------------------
