@@ -141,6 +141,17 @@ template <int V>
 __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
   const int lane = threadIdx.x & 31;
   const int C = 32 * V, c0 = lane * V;
+  // tap weights (bf16 in HBM -> fp32 in smem: no per-tap conversions) and the four LayerNorm vectors
+  __shared__ __align__(16) float s_w[27 * 32 * V];
+  __shared__ __align__(16) float s_ln[4 * 32 * V];
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) s_w[i] = __bfloat162float(p.w[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_ln[i] = p.g_cpe[i];
+    s_ln[C + i] = p.b_cpe[i];
+    s_ln[2 * C + i] = p.y1 ? p.g1[i] : 0.f;
+    s_ln[3 * C + i] = p.y1 ? p.b1[i] : 0.f;
+  }
+  __syncthreads();
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = warp0; r < p.rows; r += nwarps) {
@@ -166,11 +177,11 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
         const int32_t ni = __shfl_sync(0xffffffffu, my, k);
         float nv[V], wv[V];
         load_bf16<V>(p.xb + hat_row(ni, p.K) * C + c0, nv);
-        load_bf16<V>(p.w + k * C + c0, wv);
+        load_f32<V>(s_w + k * C + c0, wv);
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = fmaf(wv[j], nv[j], acc[j]);
       }
-      warp_ln<V>(acc, p.g_cpe, p.b_cpe, c0, 1e-5f);
+      warp_ln<V>(acc, s_ln, s_ln + C, c0, 1e-5f);
       if (p.cpe_out) {
         store_f32<V>(p.cpe_out + t * C + c0, acc);
         continue;
@@ -184,7 +195,7 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
       load_f32<V>(p.x + r * C + c0, xv);     // relay token or padding row: no CPE
     }
     if (p.y1) {
-      warp_ln<V>(xv, p.g1, p.b1, c0, 1e-5f);
+      warp_ln<V>(xv, s_ln + 2 * C, s_ln + 3 * C, c0, 1e-5f);
       store_bf16<V>(p.y1 + r * C + c0, xv);
     }
   }

@@ -420,7 +420,8 @@ class _Engine:
             f, d = g, d - 1
         blk = K * dil
         npad0 = -(-n[d0] // blk) * blk
-        x0, xb0 = Z(npad0, C0, dt=f32), Z(npad0, C0)
+        x0, xb0 = E(npad0, C0, dt=f32), E(npad0, C0)
+        x0[n[d0]:].zero_()                     # padding tokens must stay finite (they are keys/values)
         c = w['stem_proj']
         ops.gather_gemm(f, c['w'], idx=octree.ne_table(d0), KD=27, ln=c['ln'], relu=True,
                         out_y_f32=x0, out_y_bf16=xb0)
@@ -449,8 +450,10 @@ class _Engine:
 
         # ---------------- host tables for the pyramid (from the node counts) ----------------
         tabs = self._host_tables(octree, depths, nl, npad, nwin, R, K, B)
-        X, Xb = Z(int(R[-1]), C1, dt=f32), Z(int(R[-1]), C1)
+        X, Xb = E(int(R[-1]), C1, dt=f32), E(int(R[-1]), C1)
         Xl = [X[R[j]:R[j + 1]] for j in range(L)]
+        for j in range(L):                     # zero only the padding tail of each level
+            Xl[j][nl[j] + nl[j] // K + 1:].zero_()
         Xbl = [Xb[R[j]:R[j + 1]] for j in range(L)]
         tok = [octree.tokens(depths[j], npad[j]) for j in range(L)]
         ne = [octree.ne_table(dj) for dj in depths]
