@@ -127,7 +127,12 @@ def kernel_profile(model, octree_fn):
         return ('byte', rows * C * (4 + 4 + 2) + n * (27 * 4 + 2 * C))
 
     saved = {}
-    patches = {'gather_gemm': gemm_work, 'window_attn': attn_work, 'cpe_ln': cpe_work}
+    def mlp_work(A, W1, b1, W2, b2, **k):
+        M = k.get('M') or A.shape[0]
+        return ('flop', 4.0 * M * W1.shape[0] * W1.shape[1])
+
+    patches = {'gather_gemm': gemm_work, 'window_attn': attn_work, 'cpe_ln': cpe_work,
+               'mlp_fused': mlp_work}
     for name, work in patches.items():
         saved[name] = getattr(ops, name)
         setattr(ops, name, wrap(name, saved[name], work))

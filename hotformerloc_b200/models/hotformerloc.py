@@ -272,6 +272,14 @@ class PoolingWrapper(nn.Module):
 # ----------------------------------------------------------------------------
 # the kernel schedule
 # ----------------------------------------------------------------------------
+def _fused_mlp(C: int) -> bool:
+    """Which MLP path a stage uses: HFL_FUSED_MLP = comma list of channel counts (default '128':
+    the fused kernel wins at C=128; at C=256 its N=128 first GEMM is smem-bandwidth bound in
+    1-CTA mode and the two-GEMM path is as fast -- see DESIGN.md section 4)."""
+    import os
+    return str(C) in os.environ.get('HFL_FUSED_MLP', '128').split(',')
+
+
 def _bf(t):
     return t.detach().to(torch.bfloat16).contiguous()
 
@@ -370,8 +378,8 @@ class _Engine:
     # ------------------------------------------------------------------
     def _block(self, bw, x, xb, ne, tok, n, rows, n_win, C, H, K, hat, bufs, out_rows=None):
         """One OctFormer / H-OSA block on a level (6 kernels)."""
-        y, qkv, o, h = (t.view(-1)[:rows * c].view(rows, c) for t, c in
-                        ((bufs['y'], C), (bufs['qkv'], 3 * C), (bufs['o'], C), (bufs['h'], 4 * C)))
+        y, qkv, o = (t.view(-1)[:rows * c].view(rows, c) for t, c in
+                     ((bufs['y'], C), (bufs['qkv'], 3 * C), (bufs['o'], C)))
         cw, cg, cb = bw['cpe']
         ops.cpe_ln(x, xb, ne, cw, cg, cb, bw['n1'][0], bw['n1'][1], y, None, n, rows, C,
                    K if hat else 0)
@@ -379,8 +387,13 @@ class _Engine:
         ops.window_attn(qkv, o, tok, bw['rpe'], n_win, H, C, K, bw['dil'], hat, bw['bnd'], 0.25)
         ops.gather_gemm(o, bw['proj'][0], bias=bw['proj'][1], res=x, out_v_f32=x, ln=bw['n2'],
                         out_y_bf16=y)
-        ops.gather_gemm(y, bw['fc1'][0], bias=bw['fc1'][1], act=1, out_v_bf16=h)
-        ops.gather_gemm(h, bw['fc2'][0], bias=bw['fc2'][1], res=x, out_v_f32=x, out_v_bf16=xb)
+        if _fused_mlp(C):
+            ops.mlp_fused(y, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=x, out_f32=x,
+                          out_bf16=xb)
+        else:
+            h = bufs['h'].view(-1)[:rows * 4 * C].view(rows, 4 * C)
+            ops.gather_gemm(y, bw['fc1'][0], bias=bw['fc1'][1], act=1, out_v_bf16=h)
+            ops.gather_gemm(h, bw['fc2'][0], bias=bw['fc2'][1], res=x, out_v_f32=x, out_v_bf16=xb)
 
     @torch.no_grad()
     def forward(self, octree: Octree, return_intermediates: bool = False):
@@ -437,8 +450,9 @@ class _Engine:
         R = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
         max_rows = max([npad0] + rows)
         Cm = max(C0, C1)
-        bufs = dict(y=E(max_rows * Cm), qkv=E(max_rows * 3 * Cm), o=E(max_rows * Cm),
-                    h=E(max_rows * 4 * Cm))
+        bufs = dict(y=E(max_rows * Cm), qkv=E(max_rows * 3 * Cm), o=E(max_rows * Cm))
+        if not (_fused_mlp(C0) and _fused_mlp(C1)):
+            bufs['h'] = E(max_rows * 4 * Cm)
 
         # ---------------- OctFormer stage ----------------
         tok0 = octree.tokens(d0, npad0)
@@ -497,7 +511,7 @@ class _Engine:
 
         # ---------------- M x [RTSA ; H-OSA per level] (:593-633) ----------------
         T = tabs['total_rt']
-        yr, qkvr, orr, hr = E(T, C1), E(T, 3 * C1), E(T, C1), E(T, 4 * C1)
+        yr, qkvr, orr = E(T, C1), E(T, 3 * C1), E(T, C1)
         for i in range(cfg['num_blocks'][-1]):
             bw = w['rtsa'][i]
             ops.ln_rows(X, tabs['rt_rows'], T, C1, bw['n1'][0], bw['n1'][1], yr)
@@ -505,9 +519,8 @@ class _Engine:
             ops.varlen_attn(qkvr, orr, tabs['cu'], tabs['ids'], B, tabs['max_len'], H1, C1, 0.25)
             ops.gather_gemm(orr, bw['proj'][0], bias=bw['proj'][1], res=X, out_v_f32=X,
                             ln=bw['n2'], out_y_bf16=yr, out_rows=tabs['rt_rows'])
-            ops.gather_gemm(yr, bw['fc1'][0], bias=bw['fc1'][1], act=1, out_v_bf16=hr)
-            ops.gather_gemm(hr, bw['fc2'][0], bias=bw['fc2'][1], res=X, out_v_f32=X,
-                            out_rows=tabs['rt_rows'])
+            ops.mlp_fused(yr, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X, out_f32=X,
+                          out_rows=tabs['rt_rows'])
             for j in range(L):
                 self._block(w['hosa'][j][i], Xl[j], Xbl[j], ne[j], tok[j], nl[j], rows[j], nwin[j],
                             C1, H1, K, True, bufs)

@@ -35,6 +35,14 @@ def gather_gemm(A: torch.Tensor, W: torch.Tensor, *, idx: Optional[torch.Tensor]
         _p(out_rows), _s()))
 
 
+def mlp_fused(A, W1, b1, W2, b2, *, res, out_f32, out_bf16=None, out_rows=None, M=None):
+    """x[orow] = res[orow] + fc2(GELU(fc1(A))) (hfl_mlp_fused)."""
+    C = A.shape[1]
+    assert W1.shape == (4 * C, C) and W2.shape == (C, 4 * C)
+    N.check(N.lib().hfl_mlp_fused(_p(A), _p(W1), _p(b1), _p(W2), _p(b2), A.shape[0] if M is None else M,
+                                  C, _p(res), _p(out_f32), _p(out_bf16), _p(out_rows), _s()))
+
+
 def window_attn(qkv, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
     N.check(N.lib().hfl_window_attn(_p(qkv), _p(out), _p(xyzb), _p(rpe), n_win, H, C, K, dil,
                                     int(hat), bnd, float(scale), _s()))

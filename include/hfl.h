@@ -116,6 +116,14 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
                     int32_t relu, int32_t y_mapped, float* out_y_f32, void* out_y_bf16,
                     const int32_t* out_rows, void* stream);
 
+/* Fused transformer MLP: out[orow] = res[orow] + fc2(GELU(fc1(A) + b1)) + b2, hidden never
+ * leaves the SM.  W1: [4C, C] bf16, W2: [C, 4C] bf16 (nn.Linear layouts).  Replaces MLP.forward
+ * (octformer_layers.py:53-59) + the residual add of the pre-LN blocks
+ * (octformer_backbone.py:279-281, hotformerloc_backbone.py:215-216, 290-291). */
+int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, const float* b2,
+                  int64_t M, int32_t C, const float* res, float* out_f32, void* out_bf16,
+                  const int32_t* out_rows, void* stream);
+
 /* Octree window attention core (octformer_backbone.py:52-93 + RPE octformer_layers.py:144-170):
  * softmax(q k^T * scale + [same-submap mask] + RPE) v per (window, head), head_dim 16.
  * Window w holds K tokens: plain rows w*K+s; dilated rows (w/dil)*K*dil + s*dil + w%dil;

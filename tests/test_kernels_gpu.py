@@ -89,6 +89,32 @@ def test_gemm_gather_is_octree_conv(KD, Cin, N):
     assert torch.allclose(out, ref, atol=3e-3, rtol=1e-3), (out - ref).abs().max()
 
 
+@pytest.mark.parametrize('C,M,mapped', [(256, 5000, False), (128, 3001, False), (256, 777, True),
+                                        (256, 300000, False)])
+def test_mlp_fused(C, M, mapped):
+    torch.manual_seed(8)
+    y = _bf(torch.randn(M, C, device=DEV))
+    W1 = _bf(torch.randn(4 * C, C, device=DEV) / math.sqrt(C))
+    W2 = _bf(torch.randn(C, 4 * C, device=DEV) / math.sqrt(4 * C))
+    b1, b2 = torch.randn(4 * C, device=DEV) * 0.1, torch.randn(C, device=DEV) * 0.1
+    R = M + 500 if mapped else M
+    rows = torch.randperm(R, device=DEV)[:M].to(torch.int32) if mapped else None
+    x = torch.randn(R, C, device=DEV)
+    x0 = x.clone()
+    xb = torch.zeros(R, C, device=DEV, dtype=torch.bfloat16)
+    _ops().mlp_fused(y, W1, b1, W2, b2, res=x, out_f32=x, out_bf16=xb, out_rows=rows)
+    h = _bf(F.gelu(y.float() @ W1.float().t() + b1)).float()          # hidden rounded to bf16 as on chip
+    upd = h @ W2.float().t() + b2
+    ref = x0.clone()
+    if mapped:
+        ref[rows.long()] += upd
+    else:
+        ref += upd
+    assert torch.allclose(x, ref, atol=5e-3, rtol=2e-3), (x - ref).abs().max()
+    sel = rows.long() if mapped else slice(None)
+    assert torch.allclose(xb.float()[sel], ref[sel], atol=5e-2, rtol=1e-2)
+
+
 def _tokens(n_pad, n, B, K):
     xyz = torch.randint(0, 128, (n_pad, 3), dtype=torch.int16)
     bid = torch.sort(torch.randint(0, B, (n_pad,))).values.to(torch.int16)

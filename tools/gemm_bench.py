@@ -83,3 +83,24 @@ raw('qkv: bf16 out, no bias', M1, 768, 256, out_v_bf16=torch.empty(M1, 768, devi
 raw('qkv: f32 out, no bias', M1, 768, 256, out_v_f32=torch.empty(M1, 768, device=dev))
 raw('N=256 K=256 no outputs', M1, 256, 256)
 raw('N=256 K=1024 no outputs', M1, 256, 1024)
+
+# --- fused MLP ---
+def mlp(name, M, C):
+    y = torch.randn(M, C, device=dev).to(torch.bfloat16)
+    W1 = (torch.randn(4 * C, C, device=dev) / math.sqrt(C)).to(torch.bfloat16)
+    W2 = (torch.randn(C, 4 * C, device=dev) / math.sqrt(4 * C)).to(torch.bfloat16)
+    b1, b2 = torch.randn(4 * C, device=dev), torch.randn(C, device=dev)
+    x = torch.randn(M, C, device=dev)
+    xb = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    f = lambda: ops.mlp_fused(y, W1, b1, W2, b2, res=x, out_f32=x, out_bf16=xb)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(10): f()
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f'{name:28s} M={M:8d} C={C}  {ms:8.3f} ms  {16.0*M*C*C/ms/1e9:7.1f} TFLOP/s')
+
+mlp('fused MLP C256', M1, 256)
+mlp('fused MLP C128', M0, 128)
