@@ -545,6 +545,39 @@ k_gem_pool(const float* __restrict__ x, const int32_t* __restrict__ tok_off, int
   }
 }
 
+// PyramidOctGeM head (pooling.py:78-84, 98-99): Linear(no bias) + eval-mode BatchNorm1d
+// (+ F.normalize); fp32, one CTA per submap, thread = output feature.
+__global__ void __launch_bounds__(256)
+k_gem_head(const float* __restrict__ pooled, int in_dim, const float* __restrict__ w,
+           const float* __restrict__ bn_g, const float* __restrict__ bn_b,
+           const float* __restrict__ bn_mean, const float* __restrict__ bn_var, float bn_eps,
+           int out_dim, int normalize, float* __restrict__ out) {
+  extern __shared__ float gh[];
+  float* sx = gh;                 // [in_dim]
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < in_dim; i += blockDim.x) sx[i] = pooled[(size_t)b * in_dim + i];
+  __syncthreads();
+  float ss = 0.f;
+  float val[4];                   // out_dim <= 4 * blockDim
+  int nv = 0;
+  for (int o = threadIdx.x; o < out_dim; o += blockDim.x, ++nv) {
+    float a = 0.f;
+    for (int i = 0; i < in_dim; ++i) a = fmaf(w[(size_t)o * in_dim + i], sx[i], a);
+    a = (a - bn_mean[o]) * rsqrtf(bn_var[o] + bn_eps) * bn_g[o] + bn_b[o];
+    val[nv] = a;
+    ss += a * a;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float inv = normalize ? 1.0f / fmaxf(sqrtf(tot), 1e-12f) : 1.0f;
+  nv = 0;
+  for (int o = threadIdx.x; o < out_dim; o += blockDim.x, ++nv) out[(size_t)b * out_dim + o] = val[nv] * inv;
+}
+
 }  // namespace hfl
 
 using namespace hfl;
@@ -655,6 +688,15 @@ int hfl_gem_pool(const float* x, const int32_t* tok_off, int32_t B, int32_t K, i
                  float eps, float* out, int32_t ld_out, int32_t col_off, void* stream_) {
   HFL_CHECK_ARG(x && tok_off && out, "null argument");
   HFL_LAUNCH((k_gem_pool<<<B, 256, 0, (cudaStream_t)stream_>>>(x, tok_off, K, C, pw, eps, out, ld_out, col_off)));
+  return HFL_OK;
+}
+
+int hfl_gem_head(const float* pooled, int32_t B, int32_t in_dim, const float* w, const float* bn_g,
+                 const float* bn_b, const float* bn_mean, const float* bn_var, float bn_eps,
+                 int32_t out_dim, int32_t normalize, float* out, void* stream_) {
+  HFL_CHECK_ARG(pooled && w && bn_g && bn_b && bn_mean && bn_var && out, "null argument");
+  HFL_CHECK_ARG(out_dim <= 1024 && in_dim * 4 <= 48 * 1024, "head too large");
+  HFL_LAUNCH((k_gem_head<<<B, 256, in_dim * 4, (cudaStream_t)stream_>>>(pooled, in_dim, w, bn_g, bn_b, bn_mean, bn_var, bn_eps, out_dim, normalize, out)));
   return HFL_OK;
 }
 

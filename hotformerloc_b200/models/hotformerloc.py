@@ -557,12 +557,9 @@ class _Engine:
             for j in range(L):
                 ops.gem_pool(Xl[j], tabs['tok_off'][j], B, K, C1, gw['p'][j], gw['eps'], pooled,
                              L * C1, j * C1)
-            # tiny (B x 768 x 256) fp32 head: Linear(no bias) + eval-mode BatchNorm1d
             g, b, mu, var, eps = gw['bn']
-            out = torch.addmm(b - mu * g / torch.sqrt(var + eps), pooled,
-                              (gw['w'] * (g / torch.sqrt(var + eps))[:, None]).t())
-            if self.m.normalize_embeddings:
-                out = torch.nn.functional.normalize(out, dim=1)
+            out = E(B, gw['w'].shape[0], dt=f32)
+            ops.gem_head(pooled, gw['w'], g, b, mu, var, eps, self.m.normalize_embeddings, out)
         return (out, inter) if return_intermediates else out
 
     def _host_tables(self, octree, depths, nl, npad, nwin, R, K, B):

@@ -98,6 +98,12 @@ def gem_pool(x, tok_off, B, K, C, pw, eps, out, ld_out, col_off):
                                  ld_out, col_off, _s()))
 
 
+def gem_head(pooled, w, bn_g, bn_b, bn_mean, bn_var, bn_eps, normalize, out):
+    B, in_dim = pooled.shape
+    N.check(N.lib().hfl_gem_head(_p(pooled), B, in_dim, _p(w), _p(bn_g), _p(bn_b), _p(bn_mean),
+                                 _p(bn_var), float(bn_eps), w.shape[0], int(normalize), _p(out), _s()))
+
+
 def knn_topk(q: torch.Tensor, db: torch.Tensor, k: int = 25, idx_offset: int = 0):
     """Exact L2 top-k of every query row against a database shard; returns
     (squared distances [nq,k] fp32, indices [nq,k] int32) sorted by (dist, idx)."""

@@ -178,6 +178,12 @@ int hfl_mixer_tail(const float* x, const float* wc, const float* bc, const float
 int hfl_gem_pool(const float* x, const int32_t* tok_off, int32_t B, int32_t K, int32_t C, float pw,
                  float eps, float* out, int32_t ld_out, int32_t col_off, void* stream);
 
+/* PyramidOctGeM descriptor head: Linear(no bias) + eval BatchNorm1d (+ L2 normalise), fp32
+ * (pooling.py:78-84, 98-99). w: [out_dim, in_dim]. */
+int hfl_gem_head(const float* pooled, int32_t B, int32_t in_dim, const float* w, const float* bn_g,
+                 const float* bn_b, const float* bn_mean, const float* bn_var, float bn_eps,
+                 int32_t out_dim, int32_t normalize, float* out, void* stream);
+
 /* Exact L2 top-k (eval/pnv_evaluate.py:200-225, 245) on one database shard, and the
  * merge of all-gathered partial lists. */
 int hfl_knn_topk(const float* q, int32_t nq, const float* db, int32_t ndb, int32_t dim, int32_t k,

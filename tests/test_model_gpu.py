@@ -66,3 +66,28 @@ def test_stagewise_vs_oracle(name, tmp_path):
     assert errs['stem'] < 1e-2 and errs['octf0'] < 3e-2
     assert all(v < 5e-2 for v in errs.values()), errs
     assert cosine(y.float().cpu().numpy(), g.numpy()).min() >= 0.999
+
+
+def test_pyramid_octgem_head_vs_reference_golden(tmp_path):
+    """pooling=PyramidOctGeM (named in BASELINE.json north_star; not used by a shipped cfg):
+    golden produced by the reference's own code for a 3-submap Oxford batch."""
+    import json
+    from hotformerloc_b200.config.presets import MODEL_PRESETS, write_configs
+    from hotformerloc_b200.misc.utils import ModelParams
+    from hotformerloc_b200.models.model_factory import model_factory
+    from hotformerloc_b200.octree import build_batch
+    paths = write_configs(str(tmp_path), 'oxford')
+    cfg = open(paths['model_config']).read().replace('pooling=PyramidAttnPoolMixer', 'pooling=PyramidOctGeM')
+    open(paths['model_config'], 'w').write(cfg)
+    model = model_factory(ModelParams(paths['model_config']))
+    shapes = json.load(open(os.path.join(GOLDEN, 'state_shapes_oxford_gem.json')))
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == shapes
+    model.load_state_dict(M.synthetic_state_dict(shapes, mode='stress'))
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(9)
+    clouds = [M.lidar_cloud(4096, g) for _ in range(3)]
+    y = model({'octree': build_batch(clouds, 9, 2, 'cuda')})['global'].float().cpu().numpy()
+    ref = np.load(os.path.join(GOLDEN, 'descriptors_gem.npz'))['reference']
+    cos = cosine(y, ref)
+    print('gem head: min cos', cos.min(), 'max-abs', np.abs(y - ref).max())
+    assert cos.min() >= 0.999
