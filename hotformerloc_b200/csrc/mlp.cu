@@ -6,14 +6,17 @@
 // (4 KB per token at C = 256 -- a quarter of a block's traffic).  Here one CTA keeps a
 // 128-row tile of y resident in smem and walks the hidden dimension in chunks of 128:
 //     acc1[b] (TMEM, 128 cols, double buffered) = y_tile . W1[chunk]^T            (UMMA N = 128)
-//     epilogue-1 warps: +b1, GELU, bf16 -> smem H[b] in the UMMA K-major swizzled layout
-//     acc2    (TMEM, C cols)                   += H[b] . W2[:, chunk]^T            (UMMA N = C)
+//     epilogue 1: +b1, GELU, bf16 pairs stored back OVER acc1[b]  (H lives in tensor memory)
+//     acc2    (TMEM, C cols)                   += H[b] . W2[:, chunk]^T   (UMMA, A operand from TMEM)
 // and only the final (128 x C) tile leaves the SM (+b2, +residual, fp32 stream + bf16 shadow).
-// Weights stream from L2 through a 6 x 16 KB TMA ring (1 MB per tile at C = 256: the kernel is
-// bound by that L2 stream, not by HBM).  Warp roles (448 threads, 1 CTA / SM):
-//   0-3  epilogue 1 (one TMEM lane quadrant each)      8      MMA issue + TMEM alloc
-//   4-7  epilogue 2 (final tile, coalesced I/O)        9-12   y-tile producers (cp.async)
-//                                                      13     weight TMA producer
+// Keeping H out of shared memory leaves room for an 8 x 16 KB TMA weight ring (1 MB of weights
+// stream from L2 per tile at C = 256).  Warp roles (448 threads, 1 CTA / SM):
+//   0-7  epilogue warps (lane quadrant w % 4, column half w / 4): epilogue 1 of every chunk and,
+//        between the first two chunks of the next tile, epilogue 2 of the finished tile
+//   8    MMA issue + TMEM alloc      9-12  y-tile producers (cp.async)      13  weight TMA producer
+// Measured design notes (tools/micro/*.cu): a TMA load costs its issuing thread ~340 ns whatever
+// the box size, a lone UMMA N = 256 runs at 100 % / N = 128 at 90 % of the tensor peak, and the
+// A-from-TMEM operand layout is lane = row, column c = K elements (2c, 2c + 1).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -22,7 +25,7 @@
 
 namespace hfl {
 
-constexpr int ML_BM = 128, ML_CH = 128, ML_RING = 6, ML_STAGE = 16384;
+constexpr int ML_BM = 128, ML_CH = 128, ML_STAGE = 16384, ML_SLOT = 32768, ML_ISSUERS = 2;
 constexpr int ML_THREADS = 448;
 
 struct MlpParams {
@@ -34,22 +37,33 @@ struct MlpParams {
   float* out_f32;
   __nv_bfloat16* out_bf16;    // shadow or NULL
   const int32_t* out_rows;    // [M] or NULL
-  int dbg;                    // diagnostics only (HFL_MLP_DBG): 1 no GELU, 2 no H stores, 4 no proxy fence in MMA
+  int dbg;                    // diagnostics only (HFL_MLP_DBG): 1 no fp32 stores, 2 no bf16 stores, 4 no residual loads
+  long long* prof;            // diagnostics only (HFL_MLP_PROF): per-role wait/work cycles of CTA 0
 };
 
-__device__ __forceinline__ float mlp_gelu(float x) {
-  // same folded-constant erf form as the GEMM epilogue (|err| <= 2.6e-6)
-  const float t = fabsf(x), s = x * x;
-  float r = fmaf(-4.40836608e-6f, t, 1.38209148e-4f);
-  const float u = fmaf(-9.90546318e-4f, t, 8.74800568e-3f);
-  r = fmaf(r, s * 0.5f, u);
-  r = fmaf(r, t, -5.44641622e-2f);
-  r = fmaf(r, t, -4.57945084e-1f);
-  r = fmaf(r, t, -1.15144926f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(r * t));
-  const float ht = 0.5f * t;
-  return fmaf(-ht, e, fmaf(0.5f, x, ht));
+// GELU (erf form) of two values at once: the same folded-constant expansion as the GEMM
+// epilogue (|err| <= 2.6e-6), evaluated with packed FFMA2 so that the epilogue warps -- which are
+// bound by instruction issue -- spend ~9 instead of ~15 issue slots per element.  Returns the two
+// results already rounded and packed as a bf16 pair.
+__device__ __forceinline__ uint32_t mlp_gelu2_bf16(ptx::f32x2 x) {
+  using namespace ptx;
+  const f32x2 t = abs2(x), s = mul2(x, x);
+  f32x2 r = fma2(bcast2(-4.40836608e-6f), t, bcast2(1.38209148e-4f));
+  const f32x2 u = fma2(bcast2(-9.90546318e-4f), t, bcast2(8.74800568e-3f));
+  r = fma2(r, mul2(s, bcast2(0.5f)), u);
+  r = fma2(r, t, bcast2(-5.44641622e-2f));
+  r = fma2(r, t, bcast2(-4.57945084e-1f));
+  r = fma2(r, t, bcast2(-1.15144926f));
+  float a0, a1, e0, e1;
+  unpack2(mul2(r, t), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 inner = mul2(add2(x, t), bcast2(0.5f));       // 0.5 x + 0.5 |x|
+  const f32x2 y = fma2(mul2(t, bcast2(-0.5f)), pack2(e0, e1), inner);
+  float y0, y1;
+  unpack2(y, y0, y1);
+  __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // ---- coalesced staging helpers (same scheme as gemm.cu) ----
@@ -118,12 +132,13 @@ struct MlpSmem {
   static constexpr int KB1 = C / 64;                 // K blocks of GEMM 1
   static constexpr int NCH = 4 * C / ML_CH;          // hidden chunks
   static constexpr int W2S = C / 128;                // 16 KB stages per W2 K block (N2 = C rows)
+  static constexpr int RING = 4;                     // 32 KB weight slots (one hidden chunk of W1 + W2 at C = 256)
+  static constexpr int G1S = KB1 / 2;                // slots GEMM 1 consumes per chunk (two K blocks per slot)
+  static constexpr int G2S = W2S;                    // slots GEMM 2 consumes per chunk
   static constexpr int A1_BYTES = KB1 * ML_STAGE;
-  static constexpr int H_BYTES = 32768;              // single buffer: the weight ring needs the smem
-  static constexpr int W_BYTES = ML_RING * ML_STAGE;
-  static constexpr int ST_BYTES = 4 * 2048;
-  static constexpr int OFF_H = A1_BYTES;
-  static constexpr int OFF_W = OFF_H + H_BYTES;
+  static constexpr int W_BYTES = RING * ML_SLOT;
+  static constexpr int ST_BYTES = 8 * 2048;          // one transposing stage per epilogue warp
+  static constexpr int OFF_W = A1_BYTES;
   static constexpr int OFF_ST = OFF_W + W_BYTES;
   static constexpr int OFF_B1 = OFF_ST + ST_BYTES;   // b1 [4C] fp32
   static constexpr int OFF_B2 = OFF_B1 + 4 * C * 4;  // b2 [C] fp32
@@ -131,41 +146,49 @@ struct MlpSmem {
   static constexpr int TOTAL = OFF_BAR + 256;
 };
 
-template <int C>
+// cycle accounting for CTA 0 (diagnostics; prof == nullptr in production)
+#define ML_T0() const long long t0_ = PROF ? clock64() : 0
+#define ML_ACC(slot) do { if (PROF) lacc[slot] += clock64() - t0_; } while (0)
+
+template <int C, bool PROF>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
             const MlpParams p) {
   using S = MlpSmem<C>;
-  constexpr int KB1 = S::KB1, NCH = S::NCH, W2S = S::W2S;
+  constexpr int KB1 = S::KB1, NCH = S::NCH, RING = S::RING, G1S = S::G1S, G2S = S::G2S;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ptx::smem_u32(smem);
   if (base & 1023u) __trap();
-  const uint32_t sA1 = base, sH = base + S::OFF_H, sW = base + S::OFF_W, sSt = base + S::OFF_ST;
+  const uint32_t sA1 = base, sW = base + S::OFF_W, sSt = base + S::OFF_ST;
   float* s_b1 = reinterpret_cast<float*>(smem + S::OFF_B1);
   float* s_b2 = reinterpret_cast<float*>(smem + S::OFF_B2);
   const uint32_t bar = base + S::OFF_BAR;
-  const uint32_t w_full = bar, w_empty = bar + 64;            // 8 + 8 slots (ML_RING used)
-  const uint32_t a1_full = bar + 128, a1_empty = bar + 160;   // 4, 1
-  const uint32_t c1_full = bar + 168, c1_empty = bar + 184;   // acc1: 2 + 2
-  const uint32_t h_full = bar + 200, h_empty = bar + 208;     // 1 + 1 (single H buffer)
-  const uint32_t c2_full = bar + 216, c2_empty = bar + 224;   // acc2: 1 + 1
-  const uint32_t s_tmem = bar + 232;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 232);
+  const uint32_t w_full = bar, w_empty = bar + 64;            // RING + RING
+  const uint32_t a1_full = bar + 128, a1_empty = bar + 160;   // KB1 (<= 4), 1
+  const uint32_t c1_full = bar + 168;                         // acc1[2]: GEMM 1 done
+  const uint32_t h_full = bar + 184;                          // H[2] (aliases acc1): epilogue 1 done
+  const uint32_t c2_full = bar + 200, c2_empty = bar + 208;   // acc2
+  const uint32_t s_tmem = bar + 216;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 216);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + ML_BM - 1) / ML_BM;
+  const int n_my = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  const int rot = blockIdx.x % NCH;   // every CTA walks the hidden chunks in its own rotation (spreads the L2 reads)
+  long long lacc[23];                 // per-thread cycle counters (registers; dead code unless profiling)
+#pragma unroll
+  for (int i = 0; i < 23; ++i) lacc[i] = 0;
+  const long long t_role = PROF ? clock64() : 0;
 
   for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) s_b1[i] = p.b1[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_b2[i] = p.b2[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ML_RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
+    for (int s = 0; s < RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
     for (int k = 0; k < 4; ++k) ptx::mbar_init(a1_full + 8 * k, 128);
     ptx::mbar_init(a1_empty, 1);
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(c1_full + 8 * b, 1); ptx::mbar_init(c1_empty + 8 * b, 4); }
-    ptx::mbar_init(h_full, 4);
-    ptx::mbar_init(h_empty, 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(c1_full + 8 * b, 1); ptx::mbar_init(h_full + 8 * b, 8); }
     ptx::mbar_init(c2_full, 1);
-    ptx::mbar_init(c2_empty, 4);
+    ptx::mbar_init(c2_empty, 8);
     ptx::fence_barrier_init();
   }
   if (warp == 8) { ptx::tmem_alloc(s_tmem, 512); ptx::tmem_relinquish(); }
@@ -177,40 +200,49 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
 
   if (warp == 13) {
     // ===================== weight TMA producer =====================
-    if (lane == 0) {
+    // A TMA load costs its issuing thread ~340 ns whatever the box size
+    // (tools/micro/tma_issue.cu), so the stages are dealt round-robin to ML_ISSUERS lanes.
+    if (lane < ML_ISSUERS) {
       ptx::prefetch_tmap(&tm_w1);
       ptx::prefetch_tmap(&tm_w2);
       uint32_t g = 0;
-      auto load = [&](const CUtensorMap* tm, int c0, int c1) {
-        const uint32_t s = g % ML_RING, ph = (g / ML_RING) & 1;
-        ptx::mbar_wait(w_empty + 8 * s, ph ^ 1);
-        ptx::mbar_arrive_expect_tx(w_full + 8 * s, ML_STAGE);
-        ptx::tma_load_2d(sW + s * ML_STAGE, tm, w_full + 8 * s, c0, c1);
+      // every load is one 32 KB box (64 K-columns, rows, K blocks): {64, 128, 2} or {64, 256, 1}
+      auto load = [&](const CUtensorMap* tm, int row0, int kblk) {
+        if ((int)(g % (uint32_t)ML_ISSUERS) == lane) {
+          const uint32_t s = g % RING, ph = (g / RING) & 1;
+          { ML_T0(); ptx::mbar_wait_sleep(w_empty + 8 * s, ph ^ 1, 64); ML_ACC(13); }
+          ptx::mbar_arrive_expect_tx(w_full + 8 * s, ML_SLOT);
+          ptx::tma_load_3d(sW + s * ML_SLOT, tm, w_full + 8 * s, 0, row0, kblk);
+        }
         ++g;
       };
-      auto load_w1 = [&](int j) { for (int kb = 0; kb < KB1; ++kb) load(&tm_w1, kb * 64, j * ML_CH); };
-      auto load_w2 = [&](int j) {
-        for (int kb = 0; kb < 2; ++kb)
-          for (int hf = 0; hf < W2S; ++hf) load(&tm_w2, j * ML_CH + kb * 64, hf * 128);
+      auto load_w1 = [&](int j) {
+        const int jr = (j + rot) % NCH;
+        for (int h = 0; h < G1S; ++h) load(&tm_w1, jr * ML_CH, 2 * h);
       };
-      // every CTA walks the hidden chunks in a different rotation so that the 148 CTAs do not
-      // hammer the same L2 lines in lockstep
-      const int rot = blockIdx.x % NCH;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-        load_w1(rot);
+      auto load_w2 = [&](int j) {
+        const int jr = (j + rot) % NCH;
+        if (C == 256) { load(&tm_w2, 0, 2 * jr); load(&tm_w2, 0, 2 * jr + 1); }
+        else load(&tm_w2, 0, 2 * jr);
+      };
+      // same order as the MMA issuer: G1(0) G1(1) | G2(j) G1(j+2) ... (G1 runs into the next tile)
+      for (int it = 0; it < n_my; ++it) {
+        if (it == 0) { load_w1(0); load_w1(1); }
         for (int j = 0; j < NCH; ++j) {
-          if (j + 1 < NCH) load_w1((j + 1 + rot) % NCH);
-          load_w2((j + rot) % NCH);
+          load_w2(j);
+          if (j + 2 < NCH) load_w1(j + 2);
+          else if (it + 1 < n_my) load_w1(j + 2 - NCH);
         }
       }
+      if (PROF) lacc[14] = clock64() - t_role;
     }
   } else if (warp >= 9) {
     // ===================== y-tile producers =====================
     const int pt = (warp - 9) * 32 + lane;
     const int c = pt & 7, rbase = pt >> 3;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-      ptx::mbar_wait(a1_empty, (it & 1) ^ 1);
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      { ML_T0(); ptx::mbar_wait_sleep(a1_empty, (it & 1) ^ 1, 256); ML_ACC(15); }
       const int m0 = tile * ML_BM + rbase;
 #pragma unroll
       for (int kb = 0; kb < KB1; ++kb) {
@@ -226,162 +258,210 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       }
     }
     ptx::cp_async_wait<0>();
+    if (PROF) lacc[16] = clock64() - t_role;
   } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc1 = ptx::umma_idesc_bf16(ML_BM, ML_CH);
       const uint32_t idesc2 = ptx::umma_idesc_bf16(ML_BM, C);
-      uint32_t g = 0, it = 0;
-      for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-        auto gemm1 = [&](int j) {
-          const int b = j & 1;
-          const uint32_t use = it * (NCH / 2) + (j >> 1);
-          ptx::mbar_wait(c1_empty + 8 * b, (use & 1) ^ 1);
+      uint32_t g = 0;
+      // GEMM 1 of chunk j of this CTA's tile number t:  acc1[q & 1] = y_tile . W1[chunk]^T
+      auto gemm1 = [&](int t, int j) {
+        const uint32_t q = (uint32_t)t * NCH + j, b = q & 1;
+        for (int h = 0; h < G1S; ++h, ++g) {
+          if (j == 0) { ML_T0(); ptx::mbar_wait(a1_full + 8 * (2 * h), t & 1); ptx::mbar_wait(a1_full + 8 * (2 * h + 1), t & 1); ML_ACC(0); }
+          const uint32_t s = g % RING, ph = (g / RING) & 1;
+          { ML_T0(); ptx::mbar_wait(w_full + 8 * s, ph); ML_ACC(1); }
+          ML_T0();
+          ptx::fence_proxy_async();                          // the y tile was written with cp.async
           ptx::tc_fence_after();
-          for (int kb = 0; kb < KB1; ++kb, ++g) {
-            if (j == 0) ptx::mbar_wait(a1_full + 8 * kb, it & 1);
-            const uint32_t s = g % ML_RING, ph = (g / ML_RING) & 1;
-            ptx::mbar_wait(w_full + 8 * s, ph);
-            if (!(p.dbg & 4)) ptx::fence_proxy_async();
-            ptx::tc_fence_after();
-            const uint64_t ad = ptx::umma_desc_sw128(sA1 + kb * ML_STAGE);
-            const uint64_t bd = ptx::umma_desc_sw128(sW + s * ML_STAGE);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t ad = ptx::umma_desc_sw128(sA1 + (2 * h + kk) * ML_STAGE);
+            const uint64_t bd = ptx::umma_desc_sw128(sW + s * ML_SLOT + kk * ML_STAGE);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(tmem_base + b * ML_CH, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) != 0);
-            ptx::umma_commit(w_empty + 8 * s);
+              ptx::umma_bf16(tmem_base + b * ML_CH, ad + 2 * k, bd + 2 * k, idesc1, (h | kk | k) != 0);
           }
-          ptx::umma_commit(c1_full + 8 * b);
-          if (j == NCH - 1) ptx::umma_commit(a1_empty);
-        };
-        auto gemm2 = [&](int j) {
-          const uint32_t huse = it * NCH + j;
-          ptx::mbar_wait(h_full, huse & 1);
-          if (j == 0) ptx::mbar_wait(c2_empty, (it & 1) ^ 1);
+          ptx::umma_commit(w_empty + 8 * s);
+          ML_ACC(5);
+        }
+        ptx::umma_commit(c1_full + 8 * b);
+        if (j == NCH - 1) ptx::umma_commit(a1_empty);
+      };
+      // GEMM 2:  acc2 += H[q & 1] . W2[:, chunk]^T with H read from TENSOR MEMORY (bf16 pairs that
+      // epilogue 1 packed over the fp32 accumulator it had just read; K 0-63 at columns 0-31,
+      // K 64-127 at columns 64-95 of acc1[b])
+      auto gemm2 = [&](int t, int j) {
+        const uint32_t q = (uint32_t)t * NCH + j, b = q & 1;
+        { ML_T0(); ptx::mbar_wait(h_full + 8 * b, (q >> 1) & 1); ML_ACC(2); }
+        if (j == 0) { ML_T0(); ptx::mbar_wait(c2_empty, (t & 1) ^ 1); ML_ACC(3); }
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          // C = 256: one slot per K block (256 rows x 64);  C = 128: both K blocks in one slot
+          const bool fresh = C == 256 || kb == 0;
+          const uint32_t s = g % RING, ph = (g / RING) & 1;
+          if (fresh) { ML_T0(); ptx::mbar_wait(w_full + 8 * s, ph); ML_ACC(4); }
+          ML_T0();
           ptx::tc_fence_after();
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint32_t s0 = g % ML_RING;
-            for (int hf = 0; hf < W2S; ++hf) {
-              const uint32_t s = (g + hf) % ML_RING, ph = ((g + hf) / ML_RING) & 1;
-              ptx::mbar_wait(w_full + 8 * s, ph);
-            }
-            ptx::fence_proxy_async();
-            ptx::tc_fence_after();
-            const uint64_t ad = ptx::umma_desc_sw128(sH + kb * ML_STAGE);
-            const uint64_t bd = ptx::umma_desc_sw128(sW + s0 * ML_STAGE);
+          const uint32_t ta = tmem_base + b * ML_CH + kb * 64;
+          const uint64_t bd = ptx::umma_desc_sw128(sW + s * ML_SLOT + (C == 256 ? 0 : kb * ML_STAGE));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(t_acc2, ad + 2 * k, bd + 2 * k, idesc2, (j | kb | k) != 0);
-            for (int hf = 0; hf < W2S; ++hf) ptx::umma_commit(w_empty + 8 * ((g + hf) % ML_RING));
-            g += W2S;
-          }
-          ptx::umma_commit(h_empty);
-          if (j == NCH - 1) ptx::umma_commit(c2_full);
-        };
-        gemm1(0);
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ts(t_acc2, ta + 8 * k, bd + 2 * k, idesc2, (j | kb | k) != 0);
+          if (C == 256 || kb == 1) { ptx::umma_commit(w_empty + 8 * s); ++g; }
+          ML_ACC(6);
+        }
+        if (j == NCH - 1) ptx::umma_commit(c2_full);
+      };
+      // The tensor pipe executes one thread's MMAs in issue order, so GEMM 1 of chunk q + 2 (which
+      // overwrites acc1[q & 1]) is simply issued after GEMM 2 of chunk q (which reads H from it).
+      for (int it = 0; it < n_my; ++it) {
+        if (it == 0) { gemm1(0, 0); gemm1(0, 1); }
         for (int j = 0; j < NCH; ++j) {
-          if (j + 1 < NCH) gemm1(j + 1);
-          gemm2(j);
+          gemm2(it, j);
+          if (j + 2 < NCH) gemm1(it, j + 2);
+          else if (it + 1 < n_my) gemm1(it + 1, j + 2 - NCH);
         }
       }
+      if (PROF) lacc[7] = clock64() - t_role;
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ===================== epilogue 1: acc1 -> +b1, GELU -> H (smem, UMMA layout) =====================
-    const int quad = warp, r = quad * 32 + lane;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-      for (int j = 0; j < NCH; ++j) {
-        const int b = j & 1;
-        const uint32_t use = it * (NCH / 2) + (j >> 1);
-        const uint32_t huse = it * NCH + j;
-        const int jr = (j + (int)(blockIdx.x % NCH)) % NCH;    // rotated chunk (see the TMA producer)
-        ptx::mbar_wait(c1_full + 8 * b, use & 1);
-        ptx::tc_fence_after();
-        ptx::mbar_wait(h_empty, (huse & 1) ^ 1);             // GEMM 2 of the previous chunk has read H
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + b * ML_CH;
-        const uint32_t hrow = sH + (uint32_t)r * 128u;
-#pragma unroll 1
-        for (int c0 = 0; c0 < ML_CH; c0 += 32) {
-          uint32_t raw[32];
-          ptx::tmem_ld32(taddr + c0, raw);
-          ptx::tmem_ld_wait();
-          uint32_t w[16];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(s_b1 + jr * ML_CH + c0 + 4 * q);
-            float v0 = __uint_as_float(raw[4 * q]) + bb.x, v1 = __uint_as_float(raw[4 * q + 1]) + bb.y;
-            float v2 = __uint_as_float(raw[4 * q + 2]) + bb.z, v3 = __uint_as_float(raw[4 * q + 3]) + bb.w;
-            if (!(p.dbg & 1)) { v0 = mlp_gelu(v0); v1 = mlp_gelu(v1); v2 = mlp_gelu(v2); v3 = mlp_gelu(v3); }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-            w[2 * q] = *reinterpret_cast<uint32_t*>(&h0);
-            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h1);
-          }
-          const uint32_t kbase = hrow + (uint32_t)(c0 >> 6) * ML_STAGE;
-          const int ch0 = (c0 & 63) >> 3;                      // first 16-byte chunk of these 32 columns
-          if (!(p.dbg & 2))
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            ml_sts128(kbase + (uint32_t)(((ch0 + q4) ^ (r & 7)) << 4), w[4 * q4], w[4 * q4 + 1],
-                      w[4 * q4 + 2], w[4 * q4 + 3]);
-        }
-        ptx::tc_fence_before();
-        ptx::fence_proxy_async();                            // H written by the generic proxy, read by UMMA
-        __syncwarp();
-        if (lane == 0) { ptx::mbar_arrive(h_full); ptx::mbar_arrive(c1_empty + 8 * b); }
-      }
-    }
   } else {
-    // ===================== epilogue 2: acc2 + b2 + residual -> x (fp32) [+ bf16 shadow] =====================
-    const int quad = warp - 4, r = quad * 32 + lane;
-    const uint32_t stage = sSt + (uint32_t)quad * 2048u;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+    // ===================== epilogue warps 0-7 =====================
+    // warp w owns TMEM lane quadrant w % 4 (rows) and column half w / 4 of whatever it reads.
+    const int quad = warp & 3, half = warp >> 2, r = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t stage = sSt + (uint32_t)warp * 2048u;
+
+    // epilogue 1: acc1 -> +b1, GELU -> bf16 pairs written back over the accumulator (H in TMEM)
+    auto epi1 = [&](int t, int j) {
+      const uint32_t q = (uint32_t)t * NCH + j, b = q & 1;
+      const int jr = (j + rot) % NCH;
+      { ML_T0(); ptx::mbar_wait(c1_full + 8 * b, (q >> 1) & 1); ML_ACC(8); }
+      ptx::tc_fence_after();
+      ML_T0();
+      const uint32_t tacc = lane_base + b * ML_CH + half * 64;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        uint32_t raw[32];
+        long long tq0 = PROF ? clock64() : 0;
+        ptx::tmem_ld32(tacc + sl * 32, raw);
+        ptx::tmem_ld_wait();
+        if (PROF) { const long long tq = clock64(); lacc[20] += tq - tq0; tq0 = tq; }
+        uint32_t w[16];
+        const float* bias = s_b1 + jr * ML_CH + half * 64 + sl * 32;
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * qd);
+          w[2 * qd] = mlp_gelu2_bf16(ptx::add2(ptx::pack2u(raw[4 * qd], raw[4 * qd + 1]), ptx::pack2(bb.x, bb.y)));
+          w[2 * qd + 1] = mlp_gelu2_bf16(ptx::add2(ptx::pack2u(raw[4 * qd + 2], raw[4 * qd + 3]), ptx::pack2(bb.z, bb.w)));
+        }
+        if (PROF) { const long long tq = clock64(); lacc[21] += tq - tq0; tq0 = tq; }
+        ptx::tmem_st16(tacc + sl * 16, w);                   // always behind this warp's own reads
+        if (PROF) { lacc[22] += clock64() - tq0; }
+      }
+      { const long long tq0 = PROF ? clock64() : 0;
+      ptx::tmem_st_wait();
+      if (PROF) lacc[22] += clock64() - tq0; }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(h_full + 8 * b);
+      ML_ACC(9);
+    };
+
+    // epilogue 2: acc2 + b2 + residual -> x (fp32) [+ bf16 shadow], coalesced through the stage
+    auto epi2 = [&](int t) {
+      const int tile = blockIdx.x + t * gridDim.x;
       const int m = tile * ML_BM + r;
       int32_t orow = -1;
       if (m < p.M) orow = p.out_rows ? __ldg(p.out_rows + m) : m;
+      constexpr int CW = C / 2;                              // columns of this warp
+      const int cbase = half * CW;
       uint4 rbuf[8];
-      ml_res_issue(p.res, orow, C, 0, lane, rbuf);
-      ptx::mbar_wait(c2_full, it & 1);
+      ml_res_issue(p.res, (p.dbg & 4) ? -1 : orow, C, cbase, lane, rbuf);
+      { ML_T0(); ptx::mbar_wait(c2_full, t & 1); ML_ACC(10); }
       ptx::tc_fence_after();
-      const uint32_t taddr = t_acc2 + ((uint32_t)(quad * 32) << 16);
+      ML_T0();
+      const uint32_t taddr = lane_base + 256 + cbase;
 #pragma unroll 1
-      for (int c0 = 0; c0 < C; c0 += 32) {
+      for (int c0 = 0; c0 < CW; c0 += 32) {
         uint32_t raw[32];
+        long long tq0 = PROF ? clock64() : 0;
         ptx::tmem_ld32(taddr + c0, raw);
         ptx::tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_b2 + c0 + 4 * q);
-          v[4 * q] = __uint_as_float(raw[4 * q]) + bb.x;
-          v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + bb.y;
-          v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + bb.z;
-          v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + bb.w;
+        if (PROF) { const long long tq = clock64(); lacc[17] += tq - tq0; tq0 = tq; }
+        if (c0 + 32 >= CW) {                                 // acc2 fully read: GEMM 2 of the next tile may start
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(c2_empty);
         }
-        ml_res_add(stage, lane, rbuf, v);
-        if (c0 + 32 < C) ml_res_issue(p.res, orow, C, c0 + 32, lane, rbuf);
-        uint32_t w[16];
+        // Per 16-column unit: transpose acc2 + b2 through the warp's stage so that lane l holds 4
+        // consecutive columns (seg = l & 3) of rows (l >> 2) + 8 i -- the layout the residual was
+        // loaded in -- then add and store from there: fp32 as 16 B, the bf16 shadow as 8 B per lane.
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
+          __syncwarp();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) w[k] = __float_as_uint(v[u * 16 + k]);
-          ml_store_unit(stage, lane, w, reinterpret_cast<char*>(p.out_f32), orow, (size_t)C * 4,
-                        (size_t)(c0 + u * 16) * 4);
-        }
-        if (p.out_bf16) {
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
-            w[k] = *reinterpret_cast<uint32_t*>(&h);
+          for (int qd = 0; qd < 4; ++qd) {
+            const float4 bb = *reinterpret_cast<const float4*>(s_b2 + cbase + c0 + u * 16 + 4 * qd);
+            ml_sts128(ml_stage_addr(stage, lane, qd), __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd]) + bb.x),
+                      __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd + 1]) + bb.y),
+                      __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd + 2]) + bb.z),
+                      __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd + 3]) + bb.w));
           }
-          ml_store_unit(stage, lane, w, reinterpret_cast<char*>(p.out_bf16), orow, (size_t)C * 2, (size_t)c0 * 2);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = (lane >> 2) + 8 * i, seg = lane & 3;
+            const uint4 a = ml_lds128(ml_stage_addr(stage, row, seg));
+            const uint4 rr = rbuf[u * 4 + i];
+            const float o0 = __uint_as_float(a.x) + __uint_as_float(rr.x), o1 = __uint_as_float(a.y) + __uint_as_float(rr.y);
+            const float o2 = __uint_as_float(a.z) + __uint_as_float(rr.z), o3 = __uint_as_float(a.w) + __uint_as_float(rr.w);
+            const int32_t orr = __shfl_sync(0xffffffffu, orow, row);
+            if (orr >= 0) {
+              const size_t col = (size_t)(cbase + c0 + u * 16 + seg * 4);
+              if (!(p.dbg & 1))
+                *reinterpret_cast<float4*>(p.out_f32 + (size_t)orr * C + col) = make_float4(o0, o1, o2, o3);
+              if (p.out_bf16 && !(p.dbg & 2)) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+                *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)orr * C + col) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+              }
+            }
+          }
+        }
+        if (c0 + 32 < CW) ml_res_issue(p.res, (p.dbg & 4) ? -1 : orow, C, cbase + c0 + 32, lane, rbuf);
+        if (PROF) lacc[19] += clock64() - tq0;
+      }
+      ML_ACC(11);
+    };
+
+    // static schedule: the final tile of iteration t - 1 is written out between the first two
+    // chunks of iteration t, when its GEMM 2 has long finished and acc2 is about to be reused
+    for (int it = 0; it < n_my; ++it) {
+      {                                                      // pull this tile's residual rows (of this warp's column half) into L2; they are read one tile later
+        const int m = (blockIdx.x + it * gridDim.x) * ML_BM + r;
+        if (m < p.M) {
+          const int32_t orow = p.out_rows ? __ldg(p.out_rows + m) : m;
+          const char* rp = reinterpret_cast<const char*>(p.res + (size_t)orow * C + half * (C / 2));
+#pragma unroll
+          for (int k = 0; k < C * 2 / 128; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + k * 128));
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(c2_empty);
+      epi1(it, 0);
+      if (it > 0) epi2(it - 1);
+      for (int j = 1; j < NCH; ++j) epi1(it, j);
     }
+    if (n_my > 0) epi2(n_my - 1);
+    if (PROF) lacc[12] = clock64() - t_role;
+  }
+  if (PROF && blockIdx.x == 0) {
+    auto dump = [&](int a, int b) { for (int i = a; i < b; ++i) p.prof[i] = lacc[i]; };
+    if (threadIdx.x == 8 * 32) dump(0, 8);
+    if (threadIdx.x == 0) { dump(8, 13); dump(17, 23); }
+    if (threadIdx.x == 13 * 32) dump(13, 15);
+    if (threadIdx.x == 9 * 32) dump(15, 17);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -407,16 +487,17 @@ static PFN_encodeTiled2 mlp_get_encode() {
   return fn;
 }
 
-template <int C>
+template <int C, bool PROF>
 static int launch_mlp(const CUtensorMap& t1, const CUtensorMap& t2, const MlpParams& p, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    HFL_CUDA(cudaFuncSetAttribute(k_mlp_fused<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpSmem<C>::TOTAL));
+    HFL_CUDA(cudaFuncSetAttribute(k_mlp_fused<C, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  MlpSmem<C>::TOTAL));
     attr = true;
   }
   const int m_tiles = (p.M + ML_BM - 1) / ML_BM;
   const int grid = m_tiles < kSMs ? m_tiles : kSMs;
-  HFL_LAUNCH((k_mlp_fused<C><<<grid, ML_THREADS, MlpSmem<C>::TOTAL, st>>>(t1, t2, p)));
+  HFL_LAUNCH((k_mlp_fused<C, PROF><<<grid, ML_THREADS, MlpSmem<C>::TOTAL, st>>>(t1, t2, p)));
   return HFL_OK;
 }
 
@@ -437,28 +518,40 @@ int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2
   PFN_encodeTiled2 enc = mlp_get_encode();
   if (!enc) return fail(HFL_ERR_CUDA, "cuTensorMapEncodeTiled unavailable%s", "");
   CUtensorMap t1, t2;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)4 * C};
-    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
-    CUresult cr = enc(&t1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W1), dims, strides, box, es,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W1) failed%s (%lld)", "", (long long)cr);
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)4 * C, (cuuint64_t)C};
-    cuuint64_t strides[1] = {(cuuint64_t)4 * C * 2};
-    cuuint32_t box[2] = {64, 128}, es[2] = {1, 1};
-    CUresult cr = enc(&t2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W2), dims, strides, box, es,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W2) failed%s (%lld)", "", (long long)cr);
-  }
-  const char* dbg_env = getenv("HFL_MLP_DBG");
+  // 3-D views {64 K-columns, rows, K blocks of 64}: one box = consecutive 16 KB K-major UMMA tiles
+  auto make_map = [&](CUtensorMap* tm, const void* W, int rows, int cols, int box_rows, int box_kb) -> CUresult {
+    cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_kb}, es[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(W), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult cr = make_map(&t1, W1, 4 * C, C, 128, 2);
+  if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W1) failed%s (%lld)", "", (long long)cr);
+  cr = C == 256 ? make_map(&t2, W2, C, 4 * C, 256, 1) : make_map(&t2, W2, C, 4 * C, 128, 2);
+  if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W2) failed%s (%lld)", "", (long long)cr);
+  static long long* prof = nullptr;
+  const bool want_prof = getenv("HFL_MLP_PROF") != nullptr;
+  if (want_prof && !prof) cudaMalloc(&prof, 32 * sizeof(long long));
+  if (want_prof) cudaMemsetAsync(prof, 0, 32 * sizeof(long long), st);
   MlpParams p{(const __nv_bfloat16*)A, (int)M, b1, b2, res, out_f32, (__nv_bfloat16*)out_bf16, out_rows,
-              dbg_env ? atoi(dbg_env) : 0};
-  return C == 128 ? launch_mlp<128>(t1, t2, p, st) : launch_mlp<256>(t1, t2, p, st);
+              getenv("HFL_MLP_DBG") ? atoi(getenv("HFL_MLP_DBG")) : 0, want_prof ? prof : nullptr};
+  const int rc = want_prof ? (C == 128 ? launch_mlp<128, true>(t1, t2, p, st) : launch_mlp<256, true>(t1, t2, p, st))
+                           : (C == 128 ? launch_mlp<128, false>(t1, t2, p, st) : launch_mlp<256, false>(t1, t2, p, st));
+  if (want_prof && rc == HFL_OK) {
+    long long h[32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char* nm[] = {"mma:a1_full", "mma:w_full(g1)", "mma:h_full", "mma:c2_empty", "mma:w_full(g2)",
+                               "mma:issue(g1)", "mma:issue(g2)", "mma:total", "epi:c1_full", "epi:e1_work",
+                               "epi:c2_full", "epi:e2_work", "epi:total", "tma:w_empty", "tma:total",
+                               "y:a1_empty", "y:total", "e2:tmem_ld", "e2:(unused)", "e2:transpose+stores", "e1:tmem_ld", "e1:gelu", "e1:tmem_st"};
+    fprintf(stderr, "[hfl_mlp_fused prof C=%d M=%lld]", C, (long long)M);
+    for (int i = 0; i < 23; ++i) fprintf(stderr, " %s=%.1fk", nm[i], h[i] / 1e3);
+    fprintf(stderr, "\n");
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -273,11 +273,11 @@ class PoolingWrapper(nn.Module):
 # the kernel schedule
 # ----------------------------------------------------------------------------
 def _fused_mlp(C: int) -> bool:
-    """Which MLP path a stage uses: HFL_FUSED_MLP = comma list of channel counts (default '128':
-    the fused kernel wins at C=128; at C=256 its N=128 first GEMM is smem-bandwidth bound in
-    1-CTA mode and the two-GEMM path is as fast -- see DESIGN.md section 4)."""
+    """Which MLP path a stage uses: HFL_FUSED_MLP = comma list of channel counts (default
+    '128,256': the fused kernel, which keeps the hidden activation in tensor memory, beats the
+    two-GEMM path at both widths -- see DESIGN.md section 4; '' selects the two-GEMM path)."""
     import os
-    return str(C) in os.environ.get('HFL_FUSED_MLP', '128').split(',')
+    return str(C) in os.environ.get('HFL_FUSED_MLP', '128,256').split(',')
 
 
 def _bf(t):
