@@ -41,29 +41,26 @@ struct MlpParams {
   long long* prof;            // diagnostics only (HFL_MLP_PROF): per-role wait/work cycles of CTA 0
 };
 
-// GELU (erf form) of two values at once: the same folded-constant expansion as the GEMM
-// epilogue (|err| <= 2.6e-6), evaluated with packed FFMA2 so that the epilogue warps -- which are
-// bound by instruction issue -- spend ~9 instead of ~15 issue slots per element.  Returns the two
-// results already rounded and packed as a bf16 pair.
-__device__ __forceinline__ uint32_t mlp_gelu2_bf16(ptx::f32x2 x) {
+// GELU (erf form) of two values at once, given h = x / 2 (the epilogue folds the halving into
+// its bias add): GELU = h + t - t * 2^(t P(t)), t = |h| -- the same degree-4 fit as gelu_erf in
+// gemm.cu (|err| <= 9e-7), evaluated with packed FFMA2 (8 FP32-pipe ops per element, half the
+// issue slots).  Returns the two results rounded and packed as a bf16 pair.
+__device__ __forceinline__ uint32_t mlp_gelu2_bf16(ptx::f32x2 h) {
   using namespace ptx;
-  const f32x2 t = abs2(x), s = mul2(x, x);
-  f32x2 r = fma2(bcast2(-4.40836608e-6f), t, bcast2(1.38209148e-4f));
-  const f32x2 u = fma2(bcast2(-9.90546318e-4f), t, bcast2(8.74800568e-3f));
-  r = fma2(r, mul2(s, bcast2(0.5f)), u);
-  r = fma2(r, t, bcast2(-5.44641622e-2f));
-  r = fma2(r, t, bcast2(-4.57945084e-1f));
-  r = fma2(r, t, bcast2(-1.15144926f));
+  const f32x2 t = abs2(h);
+  f32x2 q = fma2(bcast2(-1.5639575e-2f), t, bcast2(1.1524727e-1f));
+  q = fma2(q, t, bcast2(-4.1725174e-1f));
+  q = fma2(q, t, bcast2(-1.8383462f));
+  q = fma2(q, t, bcast2(-2.3020070f));
   float a0, a1, e0, e1;
-  unpack2(mul2(r, t), a0, a1);
+  unpack2(mul2(q, t), a0, a1);
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-  const f32x2 inner = mul2(add2(x, t), bcast2(0.5f));       // 0.5 x + 0.5 |x|
-  const f32x2 y = fma2(mul2(t, bcast2(-0.5f)), pack2(e0, e1), inner);
+  const f32x2 y = fma2(t | 0x8000000080000000ull, pack2(e0, e1), add2(h, t));   // (-t) e + (h + t)
   float y0, y1;
   unpack2(y, y0, y1);
-  __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
-  return *reinterpret_cast<uint32_t*>(&h);
+  __nv_bfloat162 r = __floats2bfloat162_rn(y0, y1);
+  return *reinterpret_cast<uint32_t*>(&r);
 }
 
 // ---- coalesced staging helpers (same scheme as gemm.cu) ----
@@ -180,7 +177,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   for (int i = 0; i < 23; ++i) lacc[i] = 0;
   const long long t_role = PROF ? clock64() : 0;
 
-  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) s_b1[i] = p.b1[i];
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) s_b1[i] = 0.5f * p.b1[i];   // epilogue 1 works on (acc + b1) / 2
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_b2[i] = p.b2[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
@@ -354,8 +351,9 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
 #pragma unroll
         for (int qd = 0; qd < 8; ++qd) {
           const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * qd);
-          w[2 * qd] = mlp_gelu2_bf16(ptx::add2(ptx::pack2u(raw[4 * qd], raw[4 * qd + 1]), ptx::pack2(bb.x, bb.y)));
-          w[2 * qd + 1] = mlp_gelu2_bf16(ptx::add2(ptx::pack2u(raw[4 * qd + 2], raw[4 * qd + 3]), ptx::pack2(bb.z, bb.w)));
+          const ptx::f32x2 hf = ptx::bcast2(0.5f);
+          w[2 * qd] = mlp_gelu2_bf16(ptx::fma2(ptx::pack2u(raw[4 * qd], raw[4 * qd + 1]), hf, ptx::pack2(bb.x, bb.y)));
+          w[2 * qd + 1] = mlp_gelu2_bf16(ptx::fma2(ptx::pack2u(raw[4 * qd + 2], raw[4 * qd + 3]), hf, ptx::pack2(bb.z, bb.w)));
         }
         if (PROF) { const long long tq = clock64(); lacc[21] += tq - tq0; tq0 = tq; }
         ptx::tmem_st16(tacc + sl * 16, w);                   // always behind this warp's own reads
@@ -429,9 +427,13 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
                     make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
               }
             }
+            // this register is free again: fetch the same piece of the next 32-column slice
+            if (c0 + 32 < CW)
+              rbuf[u * 4 + i] = (orr >= 0 && !(p.dbg & 4))
+                                    ? *reinterpret_cast<const uint4*>(p.res + (size_t)orr * C + cbase + c0 + 32 + u * 16 + seg * 4)
+                                    : make_uint4(0u, 0u, 0u, 0u);
           }
         }
-        if (c0 + 32 < CW) ml_res_issue(p.res, (p.dbg & 4) ? -1 : orow, C, cbase + c0 + 32, lane, rbuf);
         if (PROF) lacc[19] += clock64() - tq0;
       }
       ML_ACC(11);
