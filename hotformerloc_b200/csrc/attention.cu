@@ -9,6 +9,8 @@
 //   k_varlen_attn : relay-token self-attention over ragged per-submap sequences
 // qkv is the bf16 output of the tcgen05 projection GEMM, laid out [row, 3C] as
 // [q | k | v] x [head, 16]  (octformer_backbone.py:71-72).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -17,7 +19,8 @@ namespace hfl {
 constexpr int AT_HD = 16;
 constexpr int AT_NT = 10;              // score n-tiles (8 keys each) -> up to 80 keys per pass
 constexpr int AT_KEYS = AT_NT * 8;
-constexpr int AT_RS = 48;              // smem row stride in bytes (16 bf16 + pad, conflict-free)
+constexpr int AT_RS = 48;              // smem row stride in bytes (16 bf16 + pad, conflict-free): ragged kernel
+constexpr int AT_ROW = 32;             // window kernel: unpadded 16 x bf16 rows, halves swizzled
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct WinAttnParams {
@@ -56,38 +59,48 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // CTA = one window, warp = one head.  Per window the CTA builds, once for all heads, a
-// packed table  code[row][key] = 10-bit byte offsets into the (x | y | z) RPE sub-tables,
-// or 0x80000000 for a masked pair (different submap / padding key); each warp then runs
-// QK^T -> +bias -> softmax -> PV for its head with 3 LDS + 2 FADD of bias work per score.
+// packed table  code[row][key] = 10-bit byte offsets into the (x | y | z) RPE sub-tables; every
+// sub-table ends with a zero slot (pairs without RPE) and the x table with a -inf slot that
+// masked pairs (different submap / padding key) point at, so masking costs no compare/select.
+// Each warp then runs QK^T -> +bias -> softmax -> PV for its head with 3 LDS + 4 integer ops +
+// 3 FP ops of bias work per score; the softmax row sums come out of the PV MMA (a ones column).
 // With relay tokens the K window tokens form K/16 query tiles and the single relay-token
 // query row is handled by a short CUDA-core path instead of a 1/16-full MMA tile.
 template <int NT>
 __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
   constexpr int NTC = NT * 8;          // key columns covered
   constexpr int PITCH = NTC + 4;       // code row pitch (words)
-  constexpr uint32_t MASKED = 0x80000000u;   // sign bit: offsets stay 0 (aligned, in range)
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int K = p.K, hat = p.hat, L = K + hat;
-  const int num = 2 * p.bnd + 1, sub = num + 1;          // sub-table pitch incl. a zero slot
+  const int num = 2 * p.bnd + 1, sub = num + 2;          // sub-table pitch incl. the zero and -inf slots
   float* s_rpe = reinterpret_cast<float*>(smem);                       // [H][3*sub]
   const int rpe_bytes = (p.H * 3 * sub * 4 + 15) & ~15;
   uint32_t* s_code = reinterpret_cast<uint32_t*>(smem + rpe_bytes);    // [K+1][PITCH]
   const int code_bytes = ((K + 1) * PITCH * 4 + 15) & ~15;
-  short4* s_tok = reinterpret_cast<short4*>(smem + rpe_bytes + code_bytes);   // [NTC]
-  float* s_prob = reinterpret_cast<float*>(smem + rpe_bytes + code_bytes + NTC * 8);  // [H][NTC]
-  uint8_t* wbase = smem + rpe_bytes + code_bytes + NTC * 8 + p.H * NTC * 4 +
-                   (size_t)warp * (2 * NTC * AT_RS);
-  uint8_t* sK = wbase;
-  uint8_t* sV = wbase + NTC * AT_RS;
-  const uint32_t sK_u = ptx::smem_u32(sK), sV_u = ptx::smem_u32(sV);
+  short4* s_tok = reinterpret_cast<short4*>(smem + rpe_bytes + code_bytes);   // [2][NTC]
+  float* s_prob = reinterpret_cast<float*>(smem + rpe_bytes + code_bytes + 2 * NTC * 8);  // [H][NTC]
+  // K and V of this warp's head: [2 windows in flight][K | V][NTC rows x 32 B]; the 16-byte
+  // halves of rows 4-7 of every 8 are swapped, which makes the fragment loads, ldmatrix and the
+  // 16-byte cp.async stores conflict-free without padding the rows to 48 B
+  uint8_t* wbase = smem + rpe_bytes + code_bytes + 2 * NTC * 8 + p.H * NTC * 4 +
+                   (size_t)warp * (4 * NTC * AT_ROW);
+  const uint32_t wbase_u = ptx::smem_u32(wbase);
+  auto kv_off = [](int row, int half) -> uint32_t {
+    return (uint32_t)row * AT_ROW + (uint32_t)((half ^ ((row >> 2) & 1)) << 4);
+  };
 
   for (int i = threadIdx.x; i < p.H * 3 * sub; i += blockDim.x) {
     const int h = i / (3 * sub), e = i - h * 3 * sub;
     const int axis = e / sub, k = e - axis * sub;
-    s_rpe[i] = (p.rpe && k < num) ? __ldg(p.rpe + (size_t)(axis * num + k) * p.H + h) * LOG2E : 0.f;
+    float v = 0.f;
+    if (k < num) v = p.rpe ? __ldg(p.rpe + (size_t)(axis * num + k) * p.H + h) * LOG2E : 0.f;
+    else if (k == num + 1 && axis == 0) v = -INFINITY;
+    s_rpe[i] = v;
   }
+  for (int i = threadIdx.x; i < 2 * NTC; i += blockDim.x)       // padding keys never match a submap
+    if ((i % NTC) >= L) s_tok[i] = make_short4(0, 0, 0, -2);
   const int h = warp;
   const float* tabx = s_rpe + h * 3 * sub;
   const float* taby = tabx + sub;
@@ -95,38 +108,61 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
   const int C3 = 3 * p.C;
   const float sc = p.scale * LOG2E;
   const uint32_t zero_off = (uint32_t)num * 4u;
+  const uint32_t MASKED = ((uint32_t)(num + 1) * 4u) | (zero_off << 10) | (zero_off << 20);
   const int n_mt = K / 16;
 
-  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x) {
-    __syncthreads();                              // previous window fully consumed
-    // ---- tokens of the window; K / V of this warp's head ----
-    for (int s = threadIdx.x; s < NTC; s += blockDim.x) {
-      short4 tk = make_short4(0, 0, 0, -2);
-      if (s < L) {
-        int64_t row, tok;
-        slot_row(p, w, s, row, tok);
-        tk = p.xyzb[tok >= 0 ? tok : (int64_t)w * K];      // relay token: id of the first token
-      }
-      s_tok[s] = tk;
+  // stage window w (token table for the CTA, K / V of this warp's head) into buffer `buf`
+  auto stage_window = [&](int w, int buf) {
+    for (int s = threadIdx.x; s < L; s += blockDim.x) {
+      int64_t row, tok;
+      slot_row(p, w, s, row, tok);
+      ptx::cp_async8(ptx::smem_u32(s_tok + buf * NTC + s), p.xyzb + (tok >= 0 ? tok : (int64_t)w * K));  // relay token: id of the first token
     }
+    const uint32_t kb_u = wbase_u + (uint32_t)buf * (2 * NTC * AT_ROW), vb_u = kb_u + NTC * AT_ROW;
     for (int s = lane; s < NTC; s += 32) {
       int64_t row = 0, tok;
       const bool ok = s < L;
       if (ok) slot_row(p, w, s, row, tok);
       const __nv_bfloat16* src = p.qkv + row * C3 + p.C + h * AT_HD;
-      ptx::cp_async16(sK_u + s * AT_RS, src, ok ? 16u : 0u);
-      ptx::cp_async16(sK_u + s * AT_RS + 16, src + 8, ok ? 16u : 0u);
-      ptx::cp_async16(sV_u + s * AT_RS, src + p.C, ok ? 16u : 0u);
-      ptx::cp_async16(sV_u + s * AT_RS + 16, src + p.C + 8, ok ? 16u : 0u);
+      ptx::cp_async16(kb_u + kv_off(s, 0), src, ok ? 16u : 0u);
+      ptx::cp_async16(kb_u + kv_off(s, 1), src + 8, ok ? 16u : 0u);
+      ptx::cp_async16(vb_u + kv_off(s, 0), src + p.C, ok ? 16u : 0u);
+      ptx::cp_async16(vb_u + kv_off(s, 1), src + p.C + 8, ok ? 16u : 0u);
     }
     ptx::cp_async_commit();
-    __syncthreads();
+  };
+  auto load_q = [&](int w, int mt, uint32_t (&q)[4], int64_t& row0, int64_t& row1) {
+    int64_t tk_;
+    slot_row(p, w, mt * 16 + g + hat, row0, tk_);
+    slot_row(p, w, mt * 16 + g + 8 + hat, row1, tk_);
+    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
+    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
+    q[0] = __ldg(q0 + t); q[2] = __ldg(q0 + t + 4);
+    q[1] = __ldg(q1 + t); q[3] = __ldg(q1 + t + 4);
+  };
+
+  // Software pipeline over this CTA's windows: the loads of window w + 1 are in flight while the
+  // mask/RPE code table of window w is built and its attention is computed (one CTA per SM, so
+  // nothing else would hide the global-memory latency).
+  if ((int)blockIdx.x < p.n_win) stage_window(blockIdx.x, 0);
+  int buf = 0;
+  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x, buf ^= 1) {
+    ptx::cp_async_wait<0>();
+    __syncthreads();                              // window w staged; window w - 1 fully consumed
+    if (w + (int)gridDim.x < p.n_win) stage_window(w + gridDim.x, buf ^ 1);
+    uint32_t qn[4];                               // Q fragment of the next query tile (prefetched)
+    int64_t row0n, row1n;
+    load_q(w, 0, qn, row0n, row1n);
+    const short4* tokw = s_tok + buf * NTC;
+    const uint8_t* sK = wbase + (size_t)buf * (2 * NTC * AT_ROW);
+    const uint8_t* sV = sK + NTC * AT_ROW;
+    const uint32_t sV_u = ptx::smem_u32(sV);
     // ---- packed mask / RPE-offset table: rows 0..K-1 = window tokens, row K = relay token ----
     for (int e = threadIdx.x; e < (K + hat) * NTC; e += blockDim.x) {
       const int r = e / NTC, j = e - r * NTC;
       const bool rt_row = r == K;
-      const short4 ti = s_tok[rt_row ? 0 : r + hat];
-      const short4 tj = s_tok[j];
+      const short4 ti = tokw[rt_row ? 0 : r + hat];
+      const short4 tj = tokw[j];
       uint32_t code = MASKED;
       if (j < L && ti.w == tj.w) {
         if (rt_row || (hat && j == 0) || !p.rpe) {
@@ -140,31 +176,25 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
       }
       s_code[r * PITCH + j] = code;
     }
-    ptx::cp_async_wait<0>();
     __syncthreads();
 
     // ---- K/16 query tiles of window tokens ----
+    const uint8_t* tx = reinterpret_cast<const uint8_t*>(tabx);
+    const uint8_t* ty = reinterpret_cast<const uint8_t*>(taby);
+    const uint8_t* tz = reinterpret_cast<const uint8_t*>(tabz);
     for (int mt = 0; mt < n_mt; ++mt) {
       const int r0 = mt * 16 + g, r1 = r0 + 8;               // token rows (slots r + hat)
-      int64_t row0, row1, tk_;
-      slot_row(p, w, r0 + hat, row0, tk_);
-      slot_row(p, w, r1 + hat, row1, tk_);
-      uint32_t qa[4];
-      {
-        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
-        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
-        qa[0] = __ldg(q0 + t); qa[2] = __ldg(q0 + t + 4);
-        qa[1] = __ldg(q1 + t); qa[3] = __ldg(q1 + t + 4);
-      }
+      const int64_t row0 = row0n, row1 = row1n;
+      const uint32_t qa[4] = {qn[0], qn[1], qn[2], qn[3]};
+      if (mt + 1 < n_mt) load_q(w, mt + 1, qn, row0n, row1n);
       float s[NT][4];
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
         uint32_t kb[2];
-        const uint8_t* kr = sK + (nt * 8 + g) * AT_RS + t * 4;
-        kb[0] = *reinterpret_cast<const uint32_t*>(kr);
-        kb[1] = *reinterpret_cast<const uint32_t*>(kr + 16);
+        kb[0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
+        kb[1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
         ptx::mma16816(s[nt], qa, kb);
         const uint2 c0 = *reinterpret_cast<const uint2*>(s_code + r0 * PITCH + nt * 8 + 2 * t);
         const uint2 c1 = *reinterpret_cast<const uint2*>(s_code + r1 * PITCH + nt * 8 + 2 * t);
@@ -172,10 +202,10 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t c = cc[e];
-          const float bias = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(tabx) + (c & 1023u)) +
-                             *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(taby) + ((c >> 10) & 1023u)) +
-                             *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(tabz) + ((c >> 20) & 1023u));
-          s[nt][e] = c == MASKED ? -INFINITY : fmaf(s[nt][e], sc, bias);
+          const float bx = *reinterpret_cast<const float*>(tx + (c & 1023u));      // -inf for a masked pair
+          const float by = *reinterpret_cast<const float*>(ty + ((c >> 10) & 1023u));
+          const float bz = *reinterpret_cast<const float*>(tz + (c >> 20));
+          s[nt][e] = fmaf(s[nt][e], sc, bx) + (by + bz);
         }
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
@@ -184,25 +214,19 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = fast_exp2(s[nt][0] - mx0); s[nt][1] = fast_exp2(s[nt][1] - mx0);
-        s[nt][2] = fast_exp2(s[nt][2] - mx1); s[nt][3] = fast_exp2(s[nt][3] - mx1);
-        l0 += s[nt][0] + s[nt][1];
-        l1 += s[nt][2] + s[nt][3];
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      // P = 2^(s - max) rounded to bf16; O and the row sums l both come from the PV MMAs (V gets a
+      // virtual all-ones column), so the normalisation uses exactly the probabilities that were summed
       float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t ones[2] = {0x3F803F80u, 0x3F803F80u};
 #pragma unroll
       for (int kt = 0; kt < (NT + 1) / 2; ++kt) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
-        pa[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+        pa[0] = pack_bf16(fast_exp2(s[2 * kt][0] - mx0), fast_exp2(s[2 * kt][1] - mx0));
+        pa[1] = pack_bf16(fast_exp2(s[2 * kt][2] - mx1), fast_exp2(s[2 * kt][3] - mx1));
         if (2 * kt + 1 < NT) {
-          pa[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-          pa[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+          pa[2] = pack_bf16(fast_exp2(s[2 * kt + 1][0] - mx0), fast_exp2(s[2 * kt + 1][1] - mx0));
+          pa[3] = pack_bf16(fast_exp2(s[2 * kt + 1][2] - mx1), fast_exp2(s[2 * kt + 1][3] - mx1));
         } else {
           pa[2] = pa[3] = 0u;
         }
@@ -210,13 +234,14 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
         const int mi = lane >> 3;
         int key = kt * 16 + (mi & 1) * 8 + (lane & 7);
         key = key < NTC ? key : 0;                  // second half of an odd last tile: P == 0
-        ptx::ldmatrix_x4_trans(vb, sV_u + key * AT_RS + (mi >> 1) * 16);
+        ptx::ldmatrix_x4_trans(vb, sV_u + kv_off(key, mi >> 1));
         uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
         ptx::mma16816(o[0], pa, b0);
         ptx::mma16816(o[1], pa, b1);
+        ptx::mma16816(ls, pa, ones);
       }
       // every row has at least itself unmasked, so l > 0
-      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      const float i0 = 1.f / ls[0], i1 = 1.f / ls[2];
       uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
       uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
       d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
@@ -245,8 +270,8 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
         const int j = lane + 32 * u;
         float a = -INFINITY;
         if (j < NTC && s_code[K * PITCH + j] != MASKED) {
-          const uint4* kp = reinterpret_cast<const uint4*>(sK + j * AT_RS);
-          const uint4 ka = kp[0], kb = kp[1];
+          const uint4 ka = *reinterpret_cast<const uint4*>(sK + kv_off(j, 0));
+          const uint4 kb = *reinterpret_cast<const uint4*>(sK + kv_off(j, 1));
           const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
           a = 0.f;
 #pragma unroll
@@ -277,7 +302,7 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
       const int d = lane & 15, half = lane >> 4;
       float acc = 0.f;
       for (int j = half; j < L; j += 2)
-        acc = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sV + j * AT_RS + d * 2)), acc);
+        acc = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sV + kv_off(j, d >> 3) + (d & 7) * 2)), acc);
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
       if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
     }
@@ -449,16 +474,16 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   HFL_CHECK_ARG(K % 16 == 0 && K + (hat ? 1 : 0) <= AT_KEYS, "window must be a multiple of 16 and (+relay token) fit 80 keys");
   HFL_CHECK_ARG(dil >= 1 && (!hat || dil == 1), "dilation is not used with relay tokens");
   HFL_CHECK_ARG(n_win % dil == 0, "window count must be a multiple of the dilation");
-  HFL_CHECK_ARG(bnd >= 0 && (2 * bnd + 1) * 4 < 1024, "RPE bound too large for the packed offsets");
+  HFL_CHECK_ARG(bnd >= 0 && (2 * bnd + 3) * 4 < 1024, "RPE bound too large for the packed offsets");
   WinAttnParams p;
   p.qkv = (const __nv_bfloat16*)qkv; p.out = (__nv_bfloat16*)out; p.xyzb = (const short4*)xyzb;
   p.rpe = rpe; p.n_win = (int)n_win; p.H = H; p.C = C; p.K = K; p.dil = dil; p.hat = hat;
   p.bnd = bnd; p.scale = scale;
   const int L = K + (hat ? 1 : 0);
   const int NT = (L + 7) / 8, NTC = NT * 8, PITCH = NTC + 4;
-  const int sub = 2 * bnd + 2;
-  const int smem = ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + NTC * 8 +
-                   H * NTC * 4 + H * 2 * NTC * AT_RS;
+  const int sub = 2 * bnd + 3;
+  const int smem = ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + 2 * NTC * 8 +
+                   H * NTC * 4 + H * 4 * NTC * AT_ROW;
   HFL_CHECK_ARG(smem <= 227 * 1024, "window attention tables exceed shared memory");
   int grid = (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
 #define HFL_WA_CASE(NT_)                                                                          \

@@ -63,6 +63,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
                "r"(src_bytes)
                : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
