@@ -235,6 +235,15 @@ def run_native(args, rank, world, device):
 
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
+    if args.ncu_step:
+        for i in range(args.warmup):
+            step_resident(i)
+        barrier()
+        torch.cuda.profiler.start()
+        step_resident(args.warmup)
+        barrier()
+        torch.cuda.profiler.stop()
+        return
     ms, launches = timed(step_resident, args.steps, args.warmup)
     sampler.stop_flag = True
     ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1)
@@ -349,6 +358,9 @@ def main():
     ap.add_argument('--points', type=int, default=4096)
     ap.add_argument('--cpu-sample', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--ncu-step', action='store_true',
+                    help='profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop and exit '
+                         '(use with ncu --profile-from-start off); prints no bench line')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

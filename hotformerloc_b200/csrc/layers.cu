@@ -154,18 +154,33 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
   __syncthreads();
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t r = warp0; r < p.rows; r += nwarps) {
+  // token behind a layout row (-1: relay token / padding row) and its neighbour-table entry
+  auto row_token = [&](int64_t r) -> int64_t {
+    if (r >= p.rows) return -1;
     int64_t t = r;
-    bool is_rt = false;
     if (p.K) {
       const int64_t w = r / (p.K + 1);
       const int s = (int)(r - w * (p.K + 1));
-      is_rt = s == 0;
-      t = w * p.K + s - 1;
+      t = s == 0 ? -1 : w * p.K + s - 1;
     }
+    return t < p.n ? t : -1;
+  };
+  auto load_ne = [&](int64_t t) -> int32_t {
+    return (t >= 0 && lane < 27) ? __ldg(p.ne + t * 27 + lane) : -1;
+  };
+  // the dependent chain per row is  ne -> gathers -> LN -> x;  the neighbour entries of the NEXT
+  // row and the x row of THIS row are requested before the tap loop so that only the gathers'
+  // latency is left on the chain
+  int64_t t_next = row_token(warp0);
+  int32_t my_next = load_ne(t_next);
+  for (int64_t r = warp0; r < p.rows; r += nwarps) {
+    const int64_t t = t_next;
+    const int32_t my = my_next;
+    t_next = row_token(r + nwarps);
+    my_next = load_ne(t_next);
     float xv[V];
-    if (!is_rt && t < p.n) {
-      const int32_t my = lane < 27 ? __ldg(p.ne + t * 27 + lane) : -1;
+    if (!p.cpe_out) load_f32<V>(p.x + r * C + c0, xv);
+    if (t >= 0) {
       float acc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) acc[j] = 0.f;
@@ -186,13 +201,11 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
         store_f32<V>(p.cpe_out + t * C + c0, acc);
         continue;
       }
-      load_f32<V>(p.x + r * C + c0, xv);
 #pragma unroll
       for (int j = 0; j < V; ++j) xv[j] += acc[j];
       store_f32<V>(p.x + r * C + c0, xv);
     } else {
-      if (p.cpe_out) continue;
-      load_f32<V>(p.x + r * C + c0, xv);     // relay token or padding row: no CPE
+      if (p.cpe_out) continue;               // relay token or padding row: no CPE
     }
     if (p.y1) {
       warp_ln<V>(xv, s_ln + 2 * C, s_ln + 3 * C, c0, 1e-5f);
