@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
   constexpr int NTC = NT * 8;          // key columns covered
   constexpr int PITCH = NTC + 4;       // code row pitch (words)
   extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int g = lane >> 2, t = lane & 3;
   const int K = p.K, hat = p.hat, L = K + hat;
   const int num = 2 * p.bnd + 1, sub = num + 2;          // sub-table pitch incl. the zero and -inf slots

@@ -90,7 +90,8 @@ def test_gemm_gather_is_octree_conv(KD, Cin, N):
 
 
 @pytest.mark.parametrize('C,M,mapped', [(256, 5000, False), (128, 3001, False), (256, 777, True),
-                                        (256, 300000, False)])
+                                        (256, 300000, False), (256, 100, False), (128, 1, False),
+                                        (128, 128 * 148 + 5, True), (256, 128 * 148 * 2, False)])
 def test_mlp_fused(C, M, mapped):
     torch.manual_seed(8)
     y = _bf(torch.randn(M, C, device=DEV))
