@@ -306,6 +306,13 @@ def run_native(args, rank, world, device):
         return r
     dom = max((k for k in fam if k != 'octree_build'), key=lambda k: fam[k]['ms'])
     roof = roof_of(dom)
+    try:        # DRAM bytes of this family's largest launch from the committed ncu --set full capture
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(dom)
+        if cap:
+            roof['traffic'] = cap['dram_bytes']
+            roof['traffic_source'] = f"profiles/r01_traffic.json: {cap['kernel']}, one launch under ncu"
+    except Exception:
+        pass
     roof_all = {k: {kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in roof_of(k).items()
                     if kk in ('bound', 'frac', 'tflops', 'gbs', 'ms_per_step', 'launches_per_step')}
                 for k in fam if k != 'octree_build' and (fam[k]['flop'] > 0 or fam[k]['byte'] > 0)}
