@@ -84,6 +84,40 @@ __device__ __forceinline__ void warp_ln(float (&v)[V], const float* g, const flo
   for (int j = 0; j < V; ++j) v[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
 }
 
+// Same with gamma / beta in shared memory in a "planar" layout: the V channels of a lane are split
+// into V/4 planes of [32 lanes][4 floats], so every LDS.128 of a warp covers 512 contiguous bytes
+// (a lane-major [lane][V] layout makes 32-byte lane strides: 2-way bank conflicts at V = 8).
+template <int V>
+__device__ __forceinline__ int planar_index(int c) {      // channel -> float index in the planar layout
+  const int lane = c / V, j = c % V;
+  return ((j >> 2) * 32 + lane) * 4 + (j & 3);
+}
+template <int V>
+__device__ __forceinline__ void load_planar(const float* base, int lane, float (&v)[V]) {
+#pragma unroll
+  for (int jj = 0; jj < V / 4; ++jj) {
+    const float4 f = *reinterpret_cast<const float4*>(base + (jj * 32 + lane) * 4);
+    v[4 * jj] = f.x; v[4 * jj + 1] = f.y; v[4 * jj + 2] = f.z; v[4 * jj + 3] = f.w;
+  }
+}
+template <int V>
+__device__ __forceinline__ void warp_ln_planar(float (&v)[V], const float* g, const float* b, int lane,
+                                               float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) s += v[j];
+  const float mean = warp_sum(s) / (32.f * V);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) { float d = v[j] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (32.f * V) + eps);
+  float gg[V], bb[V];
+  load_planar<V>(g, lane, gg);
+  load_planar<V>(b, lane, bb);
+#pragma unroll
+  for (int j = 0; j < V; ++j) v[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
+}
+
 // ---------------------------------------------------------------------------
 // stem: first OctreeConv (Cin = 3) on CUDA cores, one warp per leaf, lane = out channel
 // ---------------------------------------------------------------------------
@@ -141,15 +175,17 @@ template <int V>
 __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
   const int lane = threadIdx.x & 31;
   const int C = 32 * V, c0 = lane * V;
-  // tap weights (bf16 in HBM -> fp32 in smem: no per-tap conversions) and the four LayerNorm vectors
-  __shared__ __align__(16) float s_w[27 * 32 * V];
+  // tap weights stay bf16 in smem: the kernel is bound by L1/shared-memory wavefronts (ncu: l1tex
+  // 88 %), and a bf16 tap row costs 4 wavefronts per warp instead of 8; plus the four LayerNorm vectors
+  __shared__ __align__(16) __nv_bfloat16 s_w[27 * 32 * V];
   __shared__ __align__(16) float s_ln[4 * 32 * V];
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) s_w[i] = __bfloat162float(p.w[i]);
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) s_w[i] = p.w[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_ln[i] = p.g_cpe[i];
-    s_ln[C + i] = p.b_cpe[i];
-    s_ln[2 * C + i] = p.y1 ? p.g1[i] : 0.f;
-    s_ln[3 * C + i] = p.y1 ? p.b1[i] : 0.f;
+    const int q = planar_index<V>(i);
+    s_ln[q] = p.g_cpe[i];
+    s_ln[C + q] = p.b_cpe[i];
+    s_ln[2 * C + q] = p.y1 ? p.g1[i] : 0.f;
+    s_ln[3 * C + q] = p.y1 ? p.b1[i] : 0.f;
   }
   __syncthreads();
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -192,11 +228,11 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
         const int32_t ni = __shfl_sync(0xffffffffu, my, k);
         float nv[V], wv[V];
         load_bf16<V>(p.xb + hat_row(ni, p.K) * C + c0, nv);
-        load_f32<V>(s_w + k * C + c0, wv);
+        load_bf16<V>(s_w + k * C + c0, wv);
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = fmaf(wv[j], nv[j], acc[j]);
       }
-      warp_ln<V>(acc, s_ln, s_ln + C, c0, 1e-5f);
+      warp_ln_planar<V>(acc, s_ln, s_ln + C, lane, 1e-5f);
       if (p.cpe_out) {
         store_f32<V>(p.cpe_out + t * C + c0, acc);
         continue;
@@ -208,7 +244,7 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
       if (p.cpe_out) continue;               // relay token or padding row: no CPE
     }
     if (p.y1) {
-      warp_ln<V>(xv, s_ln + 2 * C, s_ln + 3 * C, c0, 1e-5f);
+      warp_ln_planar<V>(xv, s_ln + 2 * C, s_ln + 3 * C, lane, 1e-5f);
       store_bf16<V>(p.y1 + r * C + c0, xv);
     }
   }
