@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
   // K and V of this warp's head: [2 windows in flight][K | V][NTC rows x 32 B]; the 16-byte
   // halves of rows 4-7 of every 8 are swapped, which makes the fragment loads, ldmatrix and the
   // 16-byte cp.async stores conflict-free without padding the rows to 48 B
-  uint8_t* wbase = smem + rpe_bytes + code_bytes + 2 * NTC * 8 + p.H * NTC * 4 +
-                   (size_t)warp * (4 * NTC * AT_ROW);
-  const uint32_t wbase_u = ptx::smem_u32(wbase);
+  const uint32_t kv_base = (uint32_t)(rpe_bytes + code_bytes + 2 * NTC * 8 + p.H * NTC * 4);
+  const uint32_t smem_u = ptx::smem_u32(smem);
+  uint8_t* wbase = smem + kv_base + (size_t)warp * (4 * NTC * AT_ROW);
   auto kv_off = [](int row, int half) -> uint32_t {
     return (uint32_t)row * AT_ROW + (uint32_t)((half ^ ((row >> 2) & 1)) << 4);
   };
@@ -118,16 +118,21 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
       slot_row(p, w, s, row, tok);
       ptx::cp_async8(ptx::smem_u32(s_tok + buf * NTC + s), p.xyzb + (tok >= 0 ? tok : (int64_t)w * K));  // relay token: id of the first token
     }
-    const uint32_t kb_u = wbase_u + (uint32_t)buf * (2 * NTC * AT_ROW), vb_u = kb_u + NTC * AT_ROW;
-    for (int s = lane; s < NTC; s += 32) {
+    // K and V of ALL heads, cooperatively: consecutive threads fetch consecutive 16-byte pieces of one
+    // row (2H pieces = the row's K or V of every head, contiguous in qkv), so one warp instruction
+    // touches 4 cache lines instead of 32, and drop them into the owning head's (warp's) buffer
+    const int pieces = 2 * p.H;
+    for (int i = threadIdx.x; i < 2 * NTC * pieces; i += blockDim.x) {
+      const int piece = i % pieces, rest = i / pieces;
+      const int s = rest % NTC, which = rest / NTC;                  // 0 = K, 1 = V
+      const int hd = piece >> 1, half = piece & 1;
       int64_t row = 0, tok;
       const bool ok = s < L;
       if (ok) slot_row(p, w, s, row, tok);
-      const __nv_bfloat16* src = p.qkv + row * C3 + p.C + h * AT_HD;
-      ptx::cp_async16(kb_u + kv_off(s, 0), src, ok ? 16u : 0u);
-      ptx::cp_async16(kb_u + kv_off(s, 1), src + 8, ok ? 16u : 0u);
-      ptx::cp_async16(vb_u + kv_off(s, 0), src + p.C, ok ? 16u : 0u);
-      ptx::cp_async16(vb_u + kv_off(s, 1), src + p.C + 8, ok ? 16u : 0u);
+      const __nv_bfloat16* src = p.qkv + row * C3 + (which + 1) * p.C + piece * 8;
+      const uint32_t dst = smem_u + kv_base + (uint32_t)hd * (4 * NTC * AT_ROW) +
+                           (uint32_t)buf * (2 * NTC * AT_ROW) + (uint32_t)which * (NTC * AT_ROW) + kv_off(s, half);
+      ptx::cp_async16(dst, src, ok ? 16u : 0u);
     }
     ptx::cp_async_commit();
   };
@@ -300,9 +305,17 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
       for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
       __syncwarp();
       const int d = lane & 15, half = lane >> 4;
-      float acc = 0.f;
-      for (int j = half; j < L; j += 2)
-        acc = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sV + kv_off(j, d >> 3) + (d & 7) * 2)), acc);
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};                    // independent chains hide the LDS latency
+      const uint8_t* vcol = sV + (d & 7) * 2;
+#pragma unroll 2
+      for (int j0 = half; j0 < NTC; j0 += 8) {                 // padding keys: pr == 0, V == 0
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + 2 * u;
+          acc4[u] = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vcol + kv_off(j, d >> 3))), acc4[u]);
+        }
+      }
+      float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
       acc += __shfl_xor_sync(0xffffffffu, acc, 16);
       if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
     }
