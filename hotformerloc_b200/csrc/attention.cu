@@ -323,6 +323,293 @@ __global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// Two heads per warp.  The per-score loop of k_window_attn is bound by shared-memory (LSU) wavefronts,
+// three quarters of which are the RPE table look-ups (ncu source page: 41 % stall_mio).  Here the
+// tables hold fp16 PAIRS -- one 32-bit entry carries the (log2e-scaled) bias of heads 2w and 2w+1 --
+// so one look-up serves two heads: warp w handles head 2w fully (QK^T, bias, softmax, PV) while it
+// stashes the other head's summed bias (2 fp16 per register), then replays head 2w+1 from the stash.
+// 8 warps per window (H = 16), two CTAs (windows) per SM instead of a software pipeline.
+// fp16 tables: |bias error| <= 2^-11 relative per term, well below the bf16 rounding of P.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ float h_lo(uint32_t v) {
+  float f;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}" : "=f"(f) : "r"(v));
+  return f;
+}
+__device__ __forceinline__ float h_hi(uint32_t v) {
+  float f;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}" : "=f"(f) : "r"(v));
+  return f;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 2) k_window_attn2(const WinAttnParams p) {
+  constexpr int NTC = NT * 8;
+  constexpr int PITCH = NTC + 4;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int K = p.K, hat = p.hat, L = K + hat;
+  const int num = 2 * p.bnd + 1, sub = num + 2;
+  const int HP = p.H >> 1;                                                // head pairs = warps
+  uint32_t* s_rpe = reinterpret_cast<uint32_t*>(smem);                    // [HP][3][sub] fp16x2
+  const int rpe_bytes = (HP * 3 * sub * 4 + 15) & ~15;
+  uint32_t* s_code = reinterpret_cast<uint32_t*>(smem + rpe_bytes);       // [K+1][PITCH]
+  const int code_bytes = ((K + 1) * PITCH * 4 + 15) & ~15;
+  short4* s_tok = reinterpret_cast<short4*>(smem + rpe_bytes + code_bytes);            // [NTC]
+  float* s_prob = reinterpret_cast<float*>(smem + rpe_bytes + code_bytes + NTC * 8);  // [H][NTC]
+  const uint32_t kv_base = (uint32_t)(rpe_bytes + code_bytes + NTC * 8 + p.H * NTC * 4);   // [H][K | V][NTC x 32 B]
+  const uint32_t smem_u = ptx::smem_u32(smem);
+  auto kv_off = [](int row, int half) -> uint32_t {
+    return (uint32_t)row * AT_ROW + (uint32_t)((half ^ ((row >> 2) & 1)) << 4);
+  };
+
+  for (int i = threadIdx.x; i < HP * 3 * sub; i += blockDim.x) {
+    const int hp = i / (3 * sub), e = i - hp * 3 * sub;
+    const int axis = e / sub, k = e - axis * sub;
+    float a = 0.f, b = 0.f;
+    if (k < num) {
+      if (p.rpe) {
+        a = __ldg(p.rpe + (size_t)(axis * num + k) * p.H + 2 * hp) * LOG2E;
+        b = __ldg(p.rpe + (size_t)(axis * num + k) * p.H + 2 * hp + 1) * LOG2E;
+      }
+    } else if (k == num + 1 && axis == 0) {
+      a = b = -INFINITY;
+    }
+    s_rpe[i] = pack_h2(a, b);
+  }
+  for (int i = threadIdx.x; i < NTC; i += blockDim.x)
+    if (i >= L) s_tok[i] = make_short4(0, 0, 0, -2);
+  const uint8_t* tx = reinterpret_cast<const uint8_t*>(s_rpe + warp * 3 * sub);
+  const uint8_t* ty = tx + sub * 4;
+  const uint8_t* tz = ty + sub * 4;
+  const int C3 = 3 * p.C;
+  const float sc = p.scale * LOG2E;
+  const uint32_t zero_off = (uint32_t)num * 4u;
+  const uint32_t MASKED = ((uint32_t)(num + 1) * 4u) | (zero_off << 10) | (zero_off << 20);
+  const int n_mt = K / 16;
+  const uint32_t ones[2] = {0x3F803F80u, 0x3F803F80u};
+
+  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x) {
+    __syncthreads();                              // previous window fully consumed
+    for (int sl = threadIdx.x; sl < L; sl += blockDim.x) {
+      int64_t row, tok;
+      slot_row(p, w, sl, row, tok);
+      ptx::cp_async8(ptx::smem_u32(s_tok + sl), p.xyzb + (tok >= 0 ? tok : (int64_t)w * K));
+    }
+    {
+      const int pieces = 2 * p.H;
+      for (int i = threadIdx.x; i < 2 * NTC * pieces; i += blockDim.x) {
+        const int piece = i % pieces, rest = i / pieces;
+        const int sl = rest % NTC, which = rest / NTC;               // 0 = K, 1 = V
+        const int hd = piece >> 1, half = piece & 1;
+        int64_t row = 0, tok;
+        const bool ok = sl < L;
+        if (ok) slot_row(p, w, sl, row, tok);
+        const __nv_bfloat16* src = p.qkv + row * C3 + (which + 1) * p.C + piece * 8;
+        const uint32_t dst = smem_u + kv_base + (uint32_t)hd * (2 * NTC * AT_ROW) +
+                             (uint32_t)which * (NTC * AT_ROW) + kv_off(sl, half);
+        ptx::cp_async16(dst, src, ok ? 16u : 0u);
+      }
+    }
+    ptx::cp_async_commit();
+    ptx::cp_async_wait<0>();
+    __syncthreads();
+    // ---- packed mask / RPE-offset table (shared by all heads) ----
+    for (int e = threadIdx.x; e < (K + hat) * NTC; e += blockDim.x) {
+      const int r = e / NTC, j = e - r * NTC;
+      const bool rt_row = r == K;
+      const short4 ti = s_tok[rt_row ? 0 : r + hat];
+      const short4 tj = s_tok[j];
+      uint32_t code = MASKED;
+      if (j < L && ti.w == tj.w) {
+        if (rt_row || (hat && j == 0) || !p.rpe) {
+          code = zero_off | (zero_off << 10) | (zero_off << 20);
+        } else {
+          const uint32_t ox = (uint32_t)(min(max((int)ti.x - (int)tj.x, -p.bnd), p.bnd) + p.bnd) * 4u;
+          const uint32_t oy = (uint32_t)(min(max((int)ti.y - (int)tj.y, -p.bnd), p.bnd) + p.bnd) * 4u;
+          const uint32_t oz = (uint32_t)(min(max((int)ti.z - (int)tj.z, -p.bnd), p.bnd) + p.bnd) * 4u;
+          code = ox | (oy << 10) | (oz << 20);
+        }
+      }
+      s_code[r * PITCH + j] = code;
+    }
+    __syncthreads();
+
+    // ---- K/16 query tiles; per tile head 2w (with the look-ups), then head 2w+1 (from the stash) ----
+    for (int mt = 0; mt < n_mt; ++mt) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      int64_t row0, row1, tk_;
+      slot_row(p, w, r0 + hat, row0, tk_);
+      slot_row(p, w, r1 + hat, row1, tk_);
+      uint32_t stash[NT][2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * warp + hh;
+        const uint8_t* sK = smem + kv_base + (size_t)h * (2 * NTC * AT_ROW);
+        const uint32_t sV_u = smem_u + kv_base + (uint32_t)h * (2 * NTC * AT_ROW) + NTC * AT_ROW;
+        uint32_t qa[4];
+        {
+          const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
+          const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
+          qa[0] = __ldg(q0 + t); qa[2] = __ldg(q0 + t + 4);
+          qa[1] = __ldg(q1 + t); qa[3] = __ldg(q1 + t + 4);
+        }
+        float s[NT][4];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+          uint32_t kb[2];
+          kb[0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
+          kb[1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
+          ptx::mma16816(s[nt], qa, kb);
+          if (hh == 0) {
+            const uint2 c0 = *reinterpret_cast<const uint2*>(s_code + r0 * PITCH + nt * 8 + 2 * t);
+            const uint2 c1 = *reinterpret_cast<const uint2*>(s_code + r1 * PITCH + nt * 8 + 2 * t);
+            const uint32_t cc[4] = {c0.x, c0.y, c1.x, c1.y};
+            uint32_t sum[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t c = cc[e];
+              const uint32_t bx = *reinterpret_cast<const uint32_t*>(tx + (c & 1023u));   // (-inf, -inf) if masked
+              const uint32_t by = *reinterpret_cast<const uint32_t*>(ty + ((c >> 10) & 1023u));
+              const uint32_t bz = *reinterpret_cast<const uint32_t*>(tz + (c >> 20));
+              sum[e] = hadd2_u32(hadd2_u32(by, bz), bx);
+              s[nt][e] = fmaf(s[nt][e], sc, h_lo(sum[e]));
+            }
+            stash[nt][0] = __byte_perm(sum[0], sum[1], 0x7632);     // head 2w+1: (e0, e1)
+            stash[nt][1] = __byte_perm(sum[2], sum[3], 0x7632);     //            (e2, e3)
+          } else {
+            s[nt][0] = fmaf(s[nt][0], sc, h_lo(stash[nt][0]));
+            s[nt][1] = fmaf(s[nt][1], sc, h_hi(stash[nt][0]));
+            s[nt][2] = fmaf(s[nt][2], sc, h_lo(stash[nt][1]));
+            s[nt][3] = fmaf(s[nt][3], sc, h_hi(stash[nt][1]));
+          }
+          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kt = 0; kt < (NT + 1) / 2; ++kt) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16(fast_exp2(s[2 * kt][0] - mx0), fast_exp2(s[2 * kt][1] - mx0));
+          pa[1] = pack_bf16(fast_exp2(s[2 * kt][2] - mx1), fast_exp2(s[2 * kt][3] - mx1));
+          if (2 * kt + 1 < NT) {
+            pa[2] = pack_bf16(fast_exp2(s[2 * kt + 1][0] - mx0), fast_exp2(s[2 * kt + 1][1] - mx0));
+            pa[3] = pack_bf16(fast_exp2(s[2 * kt + 1][2] - mx1), fast_exp2(s[2 * kt + 1][3] - mx1));
+          } else {
+            pa[2] = pa[3] = 0u;
+          }
+          uint32_t vb[4];
+          const int mi = lane >> 3;
+          int key = kt * 16 + (mi & 1) * 8 + (lane & 7);
+          key = key < NTC ? key : 0;
+          ptx::ldmatrix_x4_trans(vb, sV_u + kv_off(key, mi >> 1));
+          uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+          ptx::mma16816(o[0], pa, b0);
+          ptx::mma16816(o[1], pa, b1);
+          ptx::mma16816(ls, pa, ones);
+        }
+        const float i0 = 1.f / ls[0], i1 = 1.f / ls[2];
+        uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
+        uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
+        d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
+        d0[t + 4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
+        d1[t] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
+        d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
+      }
+    }
+    // ---- the relay-token query row of both heads (no RPE): lanes over keys, then over (dim, half) ----
+    if (hat) {
+      const int64_t rowq = (int64_t)w * (K + 1);
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * warp + hh;
+        const uint8_t* sK = smem + kv_base + (size_t)h * (2 * NTC * AT_ROW);
+        const uint8_t* sV = sK + NTC * AT_ROW;
+        float q[AT_HD];
+        {
+          const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + rowq * C3 + h * AT_HD);
+          const uint4 a = __ldg(qp), b = __ldg(qp + 1);
+          const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+            q[2 * i] = f.x; q[2 * i + 1] = f.y;
+          }
+        }
+        float sj[(NTC + 31) / 32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < (NTC + 31) / 32; ++u) {
+          const int j = lane + 32 * u;
+          float a = -INFINITY;
+          if (j < NTC && s_code[K * PITCH + j] != MASKED) {
+            const uint4 ka = *reinterpret_cast<const uint4*>(sK + kv_off(j, 0));
+            const uint4 kb = *reinterpret_cast<const uint4*>(sK + kv_off(j, 1));
+            const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+            a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+              a = fmaf(q[2 * i], f.x, a);
+              a = fmaf(q[2 * i + 1], f.y, a);
+            }
+            a *= sc;
+          }
+          sj[u] = a;
+          mx = fmaxf(mx, a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float l = 0.f;
+        float* pr = s_prob + h * NTC;
+#pragma unroll
+        for (int u = 0; u < (NTC + 31) / 32; ++u) {
+          const int j = lane + 32 * u;
+          const float e = fast_exp2(sj[u] - mx);
+          l += e;
+          if (j < NTC) pr[j] = e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        __syncwarp();
+        const int d = lane & 15, half = lane >> 4;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* vcol = sV + (d & 7) * 2;
+#pragma unroll 2
+        for (int j0 = half; j0 < NTC; j0 += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 2 * u;
+            acc4[u] = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vcol + kv_off(j, d >> 3))), acc4[u]);
+          }
+        }
+        float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Ragged (per-submap) self-attention for the relay tokens: flash-style loop over
 // key blocks of 80; CTA = (submap, head, chunk of 256 query rows), 4 warps x 4 m-tiles.
 // ---------------------------------------------------------------------------
@@ -495,12 +782,25 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   const int L = K + (hat ? 1 : 0);
   const int NT = (L + 7) / 8, NTC = NT * 8, PITCH = NTC + 4;
   const int sub = 2 * bnd + 3;
-  const int smem = ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + 2 * NTC * 8 +
-                   H * NTC * 4 + H * 4 * NTC * AT_ROW;
+  const char* ver = getenv("HFL_ATTN_V");                  // "1": one head per warp (round-1 kernel)
+  const bool two = (H % 2 == 0) && !(ver && ver[0] == '1');
+  const int smem = two ? ((H / 2 * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + NTC * 8 +
+                             H * NTC * 4 + H * 2 * NTC * AT_ROW
+                       : ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + 2 * NTC * 8 +
+                             H * NTC * 4 + H * 4 * NTC * AT_ROW;
   HFL_CHECK_ARG(smem <= 227 * 1024, "window attention tables exceed shared memory");
   int grid = (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
 #define HFL_WA_CASE(NT_)                                                                          \
   case NT_: {                                                                                     \
+    if (two) {                                                                                    \
+      static int smem_set2 = 0;                                                                   \
+      if (smem > smem_set2) {                                                                     \
+        HFL_CUDA(cudaFuncSetAttribute(k_window_attn2<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        smem_set2 = smem;                                                                         \
+      }                                                                                           \
+      HFL_LAUNCH((k_window_attn2<NT_><<<grid, H * 16, smem, st>>>(p)));                           \
+      break;                                                                                      \
+    }                                                                                             \
     static int smem_set = 0;                                                                      \
     if (smem > smem_set) {                                                                        \
       HFL_CUDA(cudaFuncSetAttribute(k_window_attn<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
