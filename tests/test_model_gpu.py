@@ -91,3 +91,26 @@ def test_pyramid_octgem_head_vs_reference_golden(tmp_path):
     cos = cosine(y, ref)
     print('gem head: min cos', cos.min(), 'max-abs', np.abs(y - ref).max())
     assert cos.min() >= 0.999
+
+
+def test_full_size_batch_properties(tmp_path):
+    """BASELINE.json configs[1] size (256 x 4096-point submaps, Oxford cfg): size-independent
+    properties -- finite unit-norm descriptors, run-to-run bitwise determinism, and the first
+    submap's descriptor equal to what the same submap gives alone (its windows, relay tokens and
+    pooling never see another submap: batch ids mask every cross-submap pair), which ties the
+    full-size run to the golden-checked small cases."""
+    from hotformerloc_b200.octree import build_batch
+    name = 'oxford_b4_init'
+    cfg, depth, spec, seed, mode = CASES[name]
+    model, _ = native_model(cfg, case_state_dict(name), tmp_path)
+    g = torch.Generator().manual_seed(77)
+    clouds = [M.lidar_cloud(4096, g) for _ in range(256)]
+    y1 = model({'octree': build_batch(clouds, depth, 2, 'cuda')})['global'].float()
+    y2 = model({'octree': build_batch(clouds, depth, 2, 'cuda')})['global'].float()
+    assert y1.shape == (256, 256) and torch.isfinite(y1).all()
+    assert torch.equal(y1, y2)
+    assert torch.allclose(y1.norm(dim=1), torch.ones(256, device=y1.device), atol=1e-3)
+    solo = model({'octree': build_batch(clouds[:1], depth, 2, 'cuda')})['global'].float()
+    cos = torch.nn.functional.cosine_similarity(solo, y1[:1]).item()
+    print(f'submap 0 alone vs in the 256-batch: cos {cos:.7f}, max-abs {(solo - y1[:1]).abs().max().item():.2e}')
+    assert cos >= 0.9999
