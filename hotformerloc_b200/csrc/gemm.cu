@@ -30,9 +30,10 @@ constexpr int G_BM = 128;
 constexpr int G_BK = 64;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;    // 16 KB
 constexpr int G_B_BYTES = 256 * G_BK * 2;     // 32 KB (block_n <= 256)
-constexpr int G_THREADS = 416;       // 8 epilogue + 1 MMA + 4 producer warps
+constexpr int G_THREADS = 448;       // 8 epilogue + 1 MMA + 4 producer warps + 1 weight-TMA warp
 constexpr int G_PROD_THREADS = 128;
-constexpr int G_W_MMA = 8, G_W_PROD = 9;
+constexpr int G_W_MMA = 8, G_W_PROD = 9, G_W_TMA = 13;
+constexpr int G_TMA_ISSUERS = 2;     // a TMA load costs its issuing thread ~340 ns (tools/micro/tma_issue.cu)
 // streaming mode: 4 stages of (A 16 KB + B 32 KB); weight-stationary mode (Ktot*block_n*2 <=
 // 128 KB): the whole W tile lives in smem for the lifetime of the CTA and 4 stages of A stream.
 constexpr int G_STAGES_STREAM = 4;
@@ -228,7 +229,34 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp >= G_W_PROD) {
+  if (warp == G_W_TMA) {
+    // ===================== weight TMA issuer =====================
+    // Kept off the cp.async producers: the ~340 ns a thread spends per TMA instruction would sit
+    // on the critical path of the A gather (stream-mode convs run at ~0.5 us per K block).
+    if (lane < G_TMA_ISSUERS) {
+      ptx::prefetch_tmap(&tmap_w);
+      const uint32_t b_bytes = (uint32_t)BN * G_BK * 2;
+      if (WS) {
+        if (lane == 0) {                                   // resident W tile: one shot
+          ptx::mbar_arrive_expect_tx(bar_w, (uint32_t)k_blocks * b_bytes);
+          for (int kb = 0; kb < k_blocks; ++kb)
+            ptx::tma_load_2d(sB + kb * b_bytes, &tmap_w, bar_w, kb * G_BK, ws_n_blk * BN);
+        }
+      } else {
+        uint32_t g = 0;
+        for (int t = t_begin; t < t_end; t += t_step) {
+          const int n_blk = t % p.n_tiles;
+          for (int kb = 0; kb < k_blocks; ++kb, ++g) {
+            if ((int)(g % G_TMA_ISSUERS) != lane) continue;
+            const uint32_t s = g % G_STAGES, ph = (g / G_STAGES) & 1;
+            ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+            ptx::tma_load_2d(sB + s * G_B_BYTES, &tmap_w, bar_full + 8 * s, kb * G_BK, n_blk * BN);
+          }
+        }
+      }
+    }
+  } else if (warp >= G_W_PROD) {
     // ===================== A producers (+ TMA for W) =====================
     // 128 threads; thread = (16-byte chunk c of the 128-byte K-block row, rows rbase + 16 i):
     // 8 consecutive lanes fetch one full 128-byte line -> every cp.async is sector-complete.
@@ -236,15 +264,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     constexpr int RSTEP = G_PROD_THREADS / 8;            // 16
     const int pt = (warp - G_W_PROD) * 32 + lane;
     const int c = pt & 7, rbase = pt >> 3;
-    const bool tma_thread = (pt == 0);
-    if (tma_thread) ptx::prefetch_tmap(&tmap_w);
-    const uint32_t b_bytes = (uint32_t)BN * G_BK * 2;
     uint32_t g = 0;                                      // k-block counter (ring position)
-    if (WS && tma_thread) {                              // resident W tile: one shot
-      ptx::mbar_arrive_expect_tx(bar_w, (uint32_t)k_blocks * b_bytes);
-      for (int kb = 0; kb < k_blocks; ++kb)
-        ptx::tma_load_2d(sB + kb * b_bytes, &tmap_w, bar_w, kb * G_BK, ws_n_blk * BN);
-    }
     for (int t = t_begin; t < t_end; t += t_step) {
       const int m_blk = WS ? t : t / p.n_tiles, n_blk = WS ? ws_n_blk : t % p.n_tiles;
       const int m0 = m_blk * G_BM + rbase;
@@ -261,10 +281,6 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
           src_row[i] = m >= p.M ? -1 : (p.idx ? (int64_t)__ldg(p.idx + (size_t)m * p.KD + kk) : (int64_t)m);
         }
         ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        if (!WS && tma_thread) {
-          ptx::mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
-          ptx::tma_load_2d(sB + s * G_B_BYTES, &tmap_w, bar_full + 8 * s, kb * G_BK, n_blk * BN);
-        }
         const uint32_t dst = sA + s * G_A_BYTES;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
