@@ -298,6 +298,15 @@ class _Engine:
         self.sig = None
         self.w: Dict[str, object] = {}
 
+    def _level_streams(self, dev, L):
+        """HFL_LEVEL_STREAMS=1: run the pyramid levels of an H-OSA block on separate streams."""
+        import os
+        if os.environ.get('HFL_LEVEL_STREAMS', '0') != '1':
+            return None
+        if getattr(self, '_streams', None) is None or len(self._streams) < L:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
+        return self._streams[:L]
+
     def _signature(self):
         ps = list(self.m.parameters()) + list(self.m.buffers())
         return (ps[0].device, sum(p._version for p in ps), len(ps))
@@ -512,6 +521,14 @@ class _Engine:
         # ---------------- M x [RTSA ; H-OSA per level] (:593-633) ----------------
         T = tabs['total_rt']
         yr, qkvr, orr = E(T, C1), E(T, 3 * C1), E(T, C1)
+        lvl_streams = self._level_streams(dev, L)
+        if lvl_streams is not None:
+            main_stream = torch.cuda.current_stream()
+            lvl_bufs = [bufs] + [dict(y=E(rows[j] * C1), qkv=E(rows[j] * 3 * C1), o=E(rows[j] * C1))
+                                 for j in range(1, L)]
+            if 'h' in bufs:
+                for j in range(1, L):
+                    lvl_bufs[j]['h'] = E(rows[j] * 4 * C1)
         for i in range(cfg['num_blocks'][-1]):
             bw = w['rtsa'][i]
             ops.ln_rows(X, tabs['rt_rows'], T, C1, bw['n1'][0], bw['n1'][1], yr)
@@ -521,9 +538,20 @@ class _Engine:
                             ln=bw['n2'], out_y_bf16=yr, out_rows=tabs['rt_rows'])
             ops.mlp_fused(yr, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X, out_f32=X,
                           out_rows=tabs['rt_rows'])
-            for j in range(L):
-                self._block(w['hosa'][j][i], Xl[j], Xbl[j], ne[j], tok[j], nl[j], rows[j], nwin[j],
-                            C1, H1, K, True, bufs)
+            if lvl_streams is None:
+                for j in range(L):
+                    self._block(w['hosa'][j][i], Xl[j], Xbl[j], ne[j], tok[j], nl[j], rows[j], nwin[j],
+                                C1, H1, K, True, bufs)
+            else:
+                # the levels of one H-OSA block are independent (the reference runs them on three
+                # streams too, hotformerloc_backbone.py:596-618); only RTSA couples them
+                fork = main_stream.record_event()
+                for j in range(L):
+                    lvl_streams[j].wait_event(fork)
+                    with torch.cuda.stream(lvl_streams[j]):
+                        self._block(w['hosa'][j][i], Xl[j], Xbl[j], ne[j], tok[j], nl[j], rows[j],
+                                    nwin[j], C1, H1, K, True, lvl_bufs[j])
+                        main_stream.wait_event(lvl_streams[j].record_event())
         if return_intermediates:
             inter['feats'] = [Xl[j][hat_rows[j].long()].clone() for j in range(L)]
             inter['rts'] = [Xl[j][::K + 1].clone() for j in range(L)]
