@@ -11,6 +11,9 @@
 // The residual stream is fp32 (x) with a bf16 shadow (xb) that feeds gathers and GEMMs.
 // "hat" layout (hierarchical attention): K window tokens preceded by their relay token,
 //   row(token t) = t + t / K + 1,  row(RT of window w) = w * (K + 1).
+#include <stdlib.h>
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -172,7 +175,7 @@ struct CpeParams {
 };
 
 template <int V>
-__global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
+__global__ void __launch_bounds__(256, 4) k_cpe_ln(const CpeParams p) {
   const int lane = threadIdx.x & 31;
   const int C = 32 * V, c0 = lane * V;
   // tap weights stay bf16 in smem: the kernel is bound by L1/shared-memory wavefronts (ncu: l1tex
@@ -190,27 +193,36 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
   __syncthreads();
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  // token behind a layout row (-1: relay token / padding row) and its neighbour-table entry
-  auto row_token = [&](int64_t r) -> int64_t {
+  // token behind a layout row (-1: relay token / padding row) and its neighbour-table entry.
+  // All row / token indices fit 32 bits (checked by the launcher): the divisions by the runtime
+  // window size are 32-bit and happen once per row, never inside the tap loop.
+  const uint32_t K = (uint32_t)p.K, n32 = (uint32_t)p.n;
+  auto row_token = [&](int64_t r) -> int32_t {
     if (r >= p.rows) return -1;
-    int64_t t = r;
-    if (p.K) {
-      const int64_t w = r / (p.K + 1);
-      const int s = (int)(r - w * (p.K + 1));
-      t = s == 0 ? -1 : w * p.K + s - 1;
+    uint32_t t = (uint32_t)r;
+    if (K) {
+      const uint32_t w = t / (K + 1), s = t - w * (K + 1);
+      if (s == 0) return -1;
+      t = w * K + s - 1;
     }
-    return t < p.n ? t : -1;
+    return t < n32 ? (int32_t)t : -1;
   };
-  auto load_ne = [&](int64_t t) -> int32_t {
-    return (t >= 0 && lane < 27) ? __ldg(p.ne + t * 27 + lane) : -1;
+  // lane k < 27 holds the LAYOUT ROW of neighbour k of the token (-1: empty)
+  auto load_ne = [&](int32_t t) -> int32_t {
+    int32_t ni = (t >= 0 && lane < 27) ? __ldg(p.ne + (int64_t)t * 27 + lane) : -1;
+    if (K && ni >= 0) ni += (int32_t)((uint32_t)ni / K) + 1;
+    return ni;
   };
+  using Raw = typename std::conditional<V == 8, uint4, uint2>::type;
+  constexpr int TAPS = 4;                    // gathers in flight per warp
   // the dependent chain per row is  ne -> gathers -> LN -> x;  the neighbour entries of the NEXT
   // row and the x row of THIS row are requested before the tap loop so that only the gathers'
-  // latency is left on the chain
-  int64_t t_next = row_token(warp0);
+  // latency is left on the chain.  (A chunked row schedule -- 64 consecutive rows per CTA for L1
+  // reuse between Morton neighbours -- was measured: no change, the grid-strided one is kept.)
+  int32_t t_next = row_token(warp0);
   int32_t my_next = load_ne(t_next);
   for (int64_t r = warp0; r < p.rows; r += nwarps) {
-    const int64_t t = t_next;
+    const int32_t t = t_next;
     const int32_t my = my_next;
     t_next = row_token(r + nwarps);
     my_next = load_ne(t_next);
@@ -220,21 +232,36 @@ __global__ void __launch_bounds__(256) k_cpe_ln(const CpeParams p) {
       float acc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) acc[j] = 0.f;
-      // visit only the occupied neighbours (about a third of the 27 taps on lidar surfaces)
+      // visit only the occupied neighbours (about a third of the 27 taps on lidar surfaces),
+      // TAPS at a time so that their gathers overlap; taps are accumulated in ascending order
       unsigned todo = __ballot_sync(0xffffffffu, my >= 0);
       while (todo) {
-        const int k = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int32_t ni = __shfl_sync(0xffffffffu, my, k);
-        float nv[V], wv[V];
-        load_bf16<V>(p.xb + hat_row(ni, p.K) * C + c0, nv);
-        load_bf16<V>(s_w + k * C + c0, wv);
+        int k[TAPS];
+        Raw a[TAPS];
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] = fmaf(wv[j], nv[j], acc[j]);
+        for (int u = 0; u < TAPS; ++u) {
+          k[u] = __ffs(todo) - 1;              // -1 once the set is exhausted (warp-uniform)
+          todo &= todo - 1;
+          const int32_t nrow = __shfl_sync(0xffffffffu, my, k[u] & 31);
+          if (k[u] >= 0) a[u] = *reinterpret_cast<const Raw*>(p.xb + (int64_t)nrow * C + c0);
+        }
+#pragma unroll
+        for (int u = 0; u < TAPS; ++u) {
+          if (k[u] < 0) break;
+          const Raw wr = *reinterpret_cast<const Raw*>(s_w + k[u] * C + c0);
+          const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a[u]);
+          const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wr);
+#pragma unroll
+          for (int j = 0; j < V / 2; ++j) {     // bf16 pair -> two fp32 (exact)
+            acc[2 * j] = fmaf(__uint_as_float(ww[j] << 16), __uint_as_float(aw[j] << 16), acc[2 * j]);
+            acc[2 * j + 1] = fmaf(__uint_as_float(ww[j] & 0xffff0000u), __uint_as_float(aw[j] & 0xffff0000u),
+                                  acc[2 * j + 1]);
+          }
+        }
       }
       warp_ln_planar<V>(acc, s_ln, s_ln + C, lane, 1e-5f);
       if (p.cpe_out) {
-        store_f32<V>(p.cpe_out + t * C + c0, acc);
+        store_f32<V>(p.cpe_out + (int64_t)t * C + c0, acc);
         continue;
       }
 #pragma unroll
@@ -652,6 +679,7 @@ int hfl_cpe_ln(float* x, const void* xb, const int32_t* ne, const void* w, const
   HFL_CHECK_ARG(x && xb && ne && w && g_cpe && b_cpe, "null argument");
   HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
   HFL_CHECK_ARG(!y1 || (g1 && b1), "norm1 parameters missing");
+  HFL_CHECK_ARG(rows < (1ll << 31) && n < (1ll << 31) && K >= 0, "row / token indices must fit 32 bits");
   CpeParams p{x, (const __nv_bfloat16*)xb, ne, (const __nv_bfloat16*)w, g_cpe, b_cpe, g1, b1, (__nv_bfloat16*)y1, cpe_out, n, rows, K};
   if (C == 128) HFL_LAUNCH((k_cpe_ln<4><<<ROWS_GRID(rows), 256, 0, st>>>(p)));
   else HFL_LAUNCH((k_cpe_ln<8><<<ROWS_GRID(rows), 256, 0, st>>>(p)));
