@@ -270,7 +270,7 @@ def pnv_write_eval_stats(file_name, prefix, stats):
         f.write(s)
 
 
-def main(argv=None):
+def main(argv=None, evaluate_fn=None, print_fn=None, write_fn=None, results_suffix='results'):
     parser = argparse.ArgumentParser(description='Evaluate model on PointNetVLAD-protocol test sets')
     parser.add_argument('--config', type=str, required=True, help='Path to configuration file')
     parser.add_argument('--model_config', type=str, required=True,
@@ -306,10 +306,10 @@ def main(argv=None):
     prefix = 'Model Params: {}, Config: {}, Model: {}'.format(
         os.path.split(params.model_params.model_params_path)[1], os.path.split(params.params_path)[1],
         model_name)
-    stats = evaluate(model, device, params, args.log, model_name, show_progress=True)
+    stats = (evaluate_fn or evaluate)(model, device, params, args.log, model_name, show_progress=True)
     if rank == 0:
-        print_eval_stats(stats)
-        pnv_write_eval_stats(f'pnv_{params.dataset_name}_results.txt', prefix, stats)
+        (print_fn or print_eval_stats)(stats)
+        (write_fn or pnv_write_eval_stats)(f'pnv_{params.dataset_name}_{results_suffix}.txt', prefix, stats)
     if dist.is_available() and dist.is_initialized():
         dist.destroy_process_group()
 

@@ -172,3 +172,54 @@ print('ok', rank)
                         '29571', str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count('ok') == 2
+
+
+def test_evaluate_splits_bookkeeping(tmp_path, monkeypatch):
+    """eval/pnv_evaluate_splits.py mirror: per-split stats keyed by the split directory of the query
+    run, 'average' only for more than one pair, the doubly nested average over locations, the
+    report files (reference pnv_evaluate_splits.py:81-133, :335-371).  The device stages are
+    replaced by given descriptors and a brute-force numpy search; the recall numbers per pair
+    are the reference's own get_recall golden."""
+    import pickle
+    from types import SimpleNamespace
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    from hotformerloc_b200.eval import pnv_evaluate_splits as S
+    sets, vecs = recall_case()
+    gold = np.load(os.path.join(GOLDEN, 'recall.npz'))
+    sets = [dict(s) for s in sets]
+    for r, s in enumerate(sets):                       # run r lives under split 'split<r % 2>'
+        for k in s:
+            s[k] = dict(s[k], query=f'split{r % 2}/run{r}/{k}.bin')
+    by_path = {s[0]['query']: r for r, s in enumerate(sets)}
+    monkeypatch.setattr(S, 'get_latent_vectors', lambda model, data_set, device, params: vecs[by_path[data_set[0]['query']]])
+
+    def fake_get_recall(m, n, dbv, qv, query_sets, database_sets, log=False, model_name='model'):
+        d = ((qv[n][:, None, :].astype(np.float64) - dbv[m][None]) ** 2).sum(-1)
+        idx = np.argsort(d, axis=1, kind='stable')[:, :25]
+        return E.recall_from_neighbors(idx, query_sets[n], m, len(dbv[m]))
+    monkeypatch.setattr(S, 'get_recall', fake_get_recall)
+    model = SimpleNamespace(eval=lambda: None)
+    params = SimpleNamespace(dataset_name='Oxford', skip_same_run=True, dataset_folder=str(tmp_path))
+    st = S.evaluate_dataset(model, 'cpu', params, sets, sets)
+    # pairs (i, j), i != j, are stored under the split of query run j; later pairs overwrite earlier
+    assert set(st) == {'split0', 'split1', 'average'}
+    assert np.allclose(st['split1']['ave_recall'], gold['recall_2_1'])       # last pair with j == 1
+    assert np.allclose(st['split0']['ave_recall'], gold['recall_2_0'])       # last pair with j in {0, 2}
+    mean_all = np.mean([gold[f'recall_{m}_{n}'] for m in range(3) for n in range(3) if m != n], axis=0)
+    assert np.allclose(st['average']['ave_recall'], mean_all)
+    one = S.evaluate_dataset(model, 'cpu', params, sets[:2], sets[:2])
+    assert 'average' in one and len(one) == 3
+    single = S.evaluate_dataset(model, 'cpu', SimpleNamespace(dataset_name='Oxford', skip_same_run=False,
+                                                              dataset_folder='.'), sets[:1], sets[:1])
+    assert set(single) == {'split0'}                                         # one pair: no 'average'
+    for name in ('oxford', 'university', 'residential', 'business'):
+        pickle.dump(sets, open(os.path.join(tmp_path, f'{name}_evaluation_database.pickle'), 'wb'))
+        pickle.dump(sets, open(os.path.join(tmp_path, f'{name}_evaluation_query.pickle'), 'wb'))
+    stats = S.evaluate(model, 'cpu', params)
+    assert set(stats) == {'oxford', 'university', 'residential', 'business', 'average'}
+    assert np.allclose(stats['average']['average']['ave_recall'], mean_all)
+    out = os.path.join(tmp_path, 'res.txt')
+    S.pnv_write_eval_stats(out, 'prefix', stats)
+    txt = open(out).read()
+    assert 'Split: [split0]' in txt and '[average]' in txt and 'AR@1%' in txt
+    S.print_eval_stats(stats)
