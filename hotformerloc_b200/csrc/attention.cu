@@ -610,6 +610,322 @@ __global__ void __launch_bounds__(256, 2) k_window_attn2(const WinAttnParams p) 
 }
 
 // ---------------------------------------------------------------------------
+// v3: the bias of one (query, key) pair is summed ONCE for eight heads and parked in shared memory.
+// k_window_attn2 spends ~20 thread-instructions per score, half of them on the bias: three field
+// extractions + three table look-ups per pair and pair of heads, repeated by every warp.  Here a
+// build phase walks the pairs of the window once per group of 8 heads: the RPE tables hold one
+// 16-byte entry (8 x fp16, one per head) per offset, so 3 LDS.128 + 8 HADD2 give the bias of a pair for
+// all 8 heads; the sums are written in MMA-fragment order ([head][m-tile][n-tile][lane] -> 4 fp16 =
+// this lane's four scores), so the score loop of a warp (= one head) costs ONE conflict-free LDS.64
+// + 4 converts per score tile.  Masked pairs (other submap / padding key) get -inf for all heads,
+// pairs without RPE (relay-token key, disable_RPE) the zero slot -- same table convention as v2.
+// H = 16 runs as two passes of 8 heads (K/V of 8 heads staged per pass): ~80 KB of shared memory per
+// window at K = 48, two windows per SM.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 hadd2_x4(const uint4 a, const uint4 b) {
+  return make_uint4(hadd2_u32(a.x, b.x), hadd2_u32(a.y, b.y), hadd2_u32(a.z, b.z), hadd2_u32(a.w, b.w));
+}
+
+struct Win3Smem {            // byte offsets into dynamic shared memory
+  int rpe, tok, rtm, prob, bias, kv, total;
+};
+__host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd) {
+  const int L = K + hat, NT = (L + 7) / 8, NTC = NT * 8, sub = 2 * bnd + 3, passes = H / 8;
+  Win3Smem m;
+  int o = 0;
+  m.rpe = o;  o += passes * 3 * sub * 16;
+  m.tok = o;  o += NTC * 8;
+  m.rtm = o;  o += (NTC + 15) & ~15;
+  m.prob = o; o += 8 * NTC * 4;
+  o = (o + 15) & ~15;
+  m.bias = o; o += 8 * (K / 16) * NT * 256;
+  m.kv = o;   o += 8 * 2 * NTC * AT_ROW;
+  m.total = o;
+  return m;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) {
+  constexpr int NTC = NT * 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int K = p.K, hat = p.hat, L = K + hat;
+  const int num = 2 * p.bnd + 1, sub = num + 2;
+  const int passes = p.H >> 3;
+  const Win3Smem lay = win3_layout(p.H, K, hat, p.bnd);
+  uint4* s_rpe = reinterpret_cast<uint4*>(smem + lay.rpe);                // [passes][3][sub] 8 x fp16
+  short4* s_tok = reinterpret_cast<short4*>(smem + lay.tok);              // [NTC]
+  uint8_t* s_rtm = smem + lay.rtm;                                        // [NTC] relay-token row mask
+  float* s_prob = reinterpret_cast<float*>(smem + lay.prob);              // [8][NTC]
+  uint2* s_bias = reinterpret_cast<uint2*>(smem + lay.bias);              // [8][n_mt][NT][32]
+  const uint32_t smem_u = ptx::smem_u32(smem);
+  const uint32_t kv_u = smem_u + (uint32_t)lay.kv;                        // [8][K | V][NTC x 32 B]
+  auto kv_off = [](int row, int half) -> uint32_t {
+    return (uint32_t)row * AT_ROW + (uint32_t)((half ^ ((row >> 2) & 1)) << 4);
+  };
+  const int n_mt = K / 16;
+
+  // RPE tables as fp16 of bias / scale, 8 heads per entry; slot num = 0, slot num + 1 of axis 0 = -inf.
+  // The summed bias seeds the accumulator of the QK^T MMA (acc = q.k + bias / scale); the softmax scale
+  // is applied inside the exponent: p = 2^(sc * acc - sc * max), one FFMA per score.
+  const float inv_scale = 1.0f / p.scale;
+  for (int i = threadIdx.x; i < passes * 3 * sub * 4; i += blockDim.x) {
+    const int hp = i & 3, e = i >> 2;                 // head pair within the entry, entry index
+    const int k = e % sub, axis = (e / sub) % 3, ps = e / (3 * sub);
+    float a = 0.f, b = 0.f;
+    if (k < num) {
+      if (p.rpe) {
+        const float* src = p.rpe + (size_t)(axis * num + k) * p.H + ps * 8 + 2 * hp;
+        a = __ldg(src) * inv_scale;
+        b = __ldg(src + 1) * inv_scale;
+      }
+    } else if (k == num + 1 && axis == 0) {
+      a = b = -INFINITY;
+    }
+    reinterpret_cast<uint32_t*>(s_rpe)[i] = pack_h2(a, b);
+  }
+  for (int i = threadIdx.x; i < NTC; i += blockDim.x)
+    if (i >= L) s_tok[i] = make_short4(0, 0, 0, -2);
+  const int C3 = 3 * p.C;
+  const float sc = p.scale * LOG2E;
+  const uint32_t ones[2] = {0x3F803F80u, 0x3F803F80u};
+  const int o_zero = num * 16, o_inf = (num + 1) * 16;
+  const bool use_rpe = p.rpe != nullptr;
+
+  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x) {
+    // row(slot) = row_base + slot * row_step; token(slot) = tok_base + slot (hat: slot - 1, relay -> first token)
+    int64_t row_base, tok_base;
+    int row_step = 1;
+    if (hat) { row_base = (int64_t)w * (K + 1); tok_base = (int64_t)w * K - 1; }
+    else if (p.dil > 1) {
+      row_base = (int64_t)(w / p.dil) * K * p.dil + (w % p.dil);
+      row_step = p.dil;
+      tok_base = 0;
+    } else { row_base = (int64_t)w * K; tok_base = row_base; }
+    for (int ps = 0; ps < passes; ++ps) {
+      __syncthreads();                              // previous pass / window fully consumed
+      if (ps == 0) {
+        for (int sl = threadIdx.x; sl < L; sl += blockDim.x) {
+          int64_t tok = (p.dil > 1 && !hat) ? row_base + (int64_t)sl * row_step : tok_base + sl;
+          if (hat && sl == 0) tok = (int64_t)w * K;
+          ptx::cp_async8(ptx::smem_u32(s_tok + sl), p.xyzb + tok);
+        }
+      }
+      ptx::cp_async_commit();
+      // K / V of this pass's 8 heads: 16 pieces of 16 B per (slot, K | V); a half-warp per row,
+      // 16 rows per sweep of the CTA
+      {
+        const int piece = threadIdx.x & 15;
+        const __nv_bfloat16* src0 = p.qkv + p.C + ps * 128 + piece * 8;
+        const uint32_t dst0 = kv_u + (uint32_t)(piece >> 1) * (2 * NTC * AT_ROW);
+        for (int r = threadIdx.x >> 4; r < 2 * NTC; r += 16) {
+          const int which = r >= NTC, sl = r - which * NTC;            // 0 = K, 1 = V
+          const bool ok = sl < L;
+          const int64_t row = ok ? row_base + (int64_t)sl * row_step : 0;
+          ptx::cp_async16(dst0 + (uint32_t)which * (NTC * AT_ROW) + kv_off(sl, piece & 1),
+                          src0 + row * C3 + which * p.C, ok ? 16u : 0u);
+        }
+      }
+      ptx::cp_async_commit();
+      // this warp's head; the Q fragments of its first query tile (and the relay-token query row) are
+      // requested now, so that their latency hides behind the bias build
+      const int h = ps * 8 + warp;
+      const __nv_bfloat16* qh = p.qkv + h * AT_HD;
+      auto load_q = [&](int mt, uint32_t (&qf)[4]) {
+        const int64_t r0_ = row_base + (int64_t)(mt * 16 + g + hat) * row_step;
+        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(qh + r0_ * C3);
+        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(qh + (r0_ + 8 * (int64_t)row_step) * C3);
+        qf[0] = __ldg(q0 + t); qf[2] = __ldg(q0 + t + 4);
+        qf[1] = __ldg(q1 + t); qf[3] = __ldg(q1 + t + 4);
+      };
+      uint32_t qn[4];
+      load_q(0, qn);
+      uint4 qrt0 = make_uint4(0u, 0u, 0u, 0u), qrt1 = qrt0;
+      if (hat) {
+        const uint4* qp = reinterpret_cast<const uint4*>(qh + row_base * C3);
+        qrt0 = __ldg(qp);
+        qrt1 = __ldg(qp + 1);
+      }
+      if (ps == 0) {
+        ptx::cp_async_wait<1>();                    // tokens landed (K / V still in flight)
+        __syncthreads();
+        for (int j = threadIdx.x; j < NTC; j += blockDim.x) s_rtm[j] = s_tok[0].w == s_tok[j].w;
+      }
+      // ---- bias of every (query, key) pair for the 8 heads of this pass, in fragment order ----
+      {
+        const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_rpe + ps * 3 * sub);
+        for (int tile = warp; tile < n_mt * NT; tile += 8) {
+          const int mt = tile / NT, nt = tile - mt * NT;
+          const short4 ti[2] = {s_tok[mt * 16 + g + hat], s_tok[mt * 16 + g + 8 + hat]};
+          const int c0 = nt * 8 + 2 * t;
+          const short4 tj[2] = {s_tok[c0], s_tok[c0 + 1]};
+          uint4 sum[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const short4 a = ti[e >> 1], b = tj[e & 1];
+            int ox = o_inf, oy = o_zero, oz = o_zero;
+            if (a.w == b.w) {
+              ox = o_zero;
+              if (use_rpe && !(hat && c0 + (e & 1) == 0)) {
+                ox = (min(max((int)a.x - (int)b.x, -p.bnd), p.bnd) + p.bnd) * 16;
+                oy = (min(max((int)a.y - (int)b.y, -p.bnd), p.bnd) + p.bnd) * 16;
+                oz = (min(max((int)a.z - (int)b.z, -p.bnd), p.bnd) + p.bnd) * 16;
+              }
+            }
+            const uint4 bx = *reinterpret_cast<const uint4*>(tab + ox);
+            const uint4 by = *reinterpret_cast<const uint4*>(tab + sub * 16 + oy);
+            const uint4 bz = *reinterpret_cast<const uint4*>(tab + 2 * sub * 16 + oz);
+            sum[e] = hadd2_x4(hadd2_x4(by, bz), bx);
+          }
+          uint2* dst = s_bias + (size_t)(mt * NT + nt) * 32 + lane;
+          const size_t hstride = (size_t)n_mt * NT * 32;
+          const uint32_t* s0 = reinterpret_cast<const uint32_t*>(&sum[0]);
+          const uint32_t* s1 = reinterpret_cast<const uint32_t*>(&sum[1]);
+          const uint32_t* s2 = reinterpret_cast<const uint32_t*>(&sum[2]);
+          const uint32_t* s3 = reinterpret_cast<const uint32_t*>(&sum[3]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            dst[(2 * k) * hstride] = make_uint2(__byte_perm(s0[k], s1[k], 0x5410), __byte_perm(s2[k], s3[k], 0x5410));
+            dst[(2 * k + 1) * hstride] = make_uint2(__byte_perm(s0[k], s1[k], 0x7632), __byte_perm(s2[k], s3[k], 0x7632));
+          }
+        }
+      }
+      ptx::cp_async_wait<0>();
+      __syncthreads();
+
+      // ---- warp = head: K/16 query tiles ----
+      const uint32_t sK_u = kv_u + (uint32_t)warp * (2 * NTC * AT_ROW);
+      const uint32_t sV_u = sK_u + NTC * AT_ROW;
+      const uint8_t* sK = smem + lay.kv + (size_t)warp * (2 * NTC * AT_ROW);
+      const uint2* bias_h = s_bias + (size_t)warp * n_mt * NT * 32 + lane;
+      for (int mt = 0; mt < n_mt; ++mt) {
+        const int64_t row0 = row_base + (int64_t)(mt * 16 + g + hat) * row_step;
+        const int64_t row1 = row0 + 8 * (int64_t)row_step;
+        uint32_t qa[4] = {qn[0], qn[1], qn[2], qn[3]};
+        if (mt + 1 < n_mt) load_q(mt + 1, qn);       // next tile's Q in flight during this tile
+        float s[NT][4];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint2 bb = bias_h[(mt * NT + nt) * 32];
+          s[nt][0] = h_lo(bb.x); s[nt][1] = h_hi(bb.x);
+          s[nt][2] = h_lo(bb.y); s[nt][3] = h_hi(bb.y);
+          uint32_t kb[2];
+          kb[0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
+          kb[1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
+          ptx::mma16816(s[nt], qa, kb);
+          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        mx0 *= sc;                                   // exponent = sc * acc - sc * max
+        mx1 *= sc;
+        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kt = 0; kt < (NT + 1) / 2; ++kt) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16(fast_exp2(fmaf(s[2 * kt][0], sc, -mx0)), fast_exp2(fmaf(s[2 * kt][1], sc, -mx0)));
+          pa[1] = pack_bf16(fast_exp2(fmaf(s[2 * kt][2], sc, -mx1)), fast_exp2(fmaf(s[2 * kt][3], sc, -mx1)));
+          if (2 * kt + 1 < NT) {
+            pa[2] = pack_bf16(fast_exp2(fmaf(s[2 * kt + 1][0], sc, -mx0)), fast_exp2(fmaf(s[2 * kt + 1][1], sc, -mx0)));
+            pa[3] = pack_bf16(fast_exp2(fmaf(s[2 * kt + 1][2], sc, -mx1)), fast_exp2(fmaf(s[2 * kt + 1][3], sc, -mx1)));
+          } else {
+            pa[2] = pa[3] = 0u;
+          }
+          uint32_t vb[4];
+          const int mi = lane >> 3;
+          int key = kt * 16 + (mi & 1) * 8 + (lane & 7);
+          key = key < NTC ? key : 0;
+          ptx::ldmatrix_x4_trans(vb, sV_u + kv_off(key, mi >> 1));
+          uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+          ptx::mma16816(o[0], pa, b0);
+          ptx::mma16816(o[1], pa, b1);
+          ptx::mma16816(ls, pa, ones);
+        }
+        const float i0 = 1.f / ls[0], i1 = 1.f / ls[2];
+        uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
+        uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
+        d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
+        d0[t + 4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
+        d1[t] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
+        d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
+      }
+      // ---- the relay-token query row of this head (no RPE): lanes over keys, then over (dim, half) ----
+      if (hat) {
+        const int64_t rowq = row_base;
+        const uint8_t* sV = sK + NTC * AT_ROW;
+        float q[AT_HD];
+        {
+          const uint4 a = qrt0, b = qrt1;
+          const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+            q[2 * i] = f.x; q[2 * i + 1] = f.y;
+          }
+        }
+        float sj[(NTC + 31) / 32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < (NTC + 31) / 32; ++u) {
+          const int j = lane + 32 * u;
+          float a = -INFINITY;
+          if (j < NTC && s_rtm[j]) {
+            const uint4 ka = *reinterpret_cast<const uint4*>(sK + kv_off(j, 0));
+            const uint4 kb = *reinterpret_cast<const uint4*>(sK + kv_off(j, 1));
+            const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+            a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+              a = fmaf(q[2 * i], f.x, a);
+              a = fmaf(q[2 * i + 1], f.y, a);
+            }
+            a *= sc;
+          }
+          sj[u] = a;
+          mx = fmaxf(mx, a);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float l = 0.f;
+        float* pr = s_prob + warp * NTC;
+#pragma unroll
+        for (int u = 0; u < (NTC + 31) / 32; ++u) {
+          const int j = lane + 32 * u;
+          const float e = fast_exp2(sj[u] - mx);
+          l += e;
+          if (j < NTC) pr[j] = e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        __syncwarp();
+        const int d = lane & 15, half = lane >> 4;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* vcol = sV + (d & 7) * 2;
+#pragma unroll 2
+        for (int j0 = half; j0 < NTC; j0 += 8) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + 2 * u;
+            acc4[u] = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vcol + kv_off(j, d >> 3))), acc4[u]);
+          }
+        }
+        float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Ragged (per-submap) self-attention for the relay tokens: flash-style loop over
 // key blocks of 80; CTA = (submap, head, chunk of 256 query rows), 4 warps x 4 m-tiles.
 // ---------------------------------------------------------------------------
@@ -782,8 +1098,30 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   const int L = K + (hat ? 1 : 0);
   const int NT = (L + 7) / 8, NTC = NT * 8, PITCH = NTC + 4;
   const int sub = 2 * bnd + 3;
-  const char* ver = getenv("HFL_ATTN_V");                  // "1": one head per warp (round-1 kernel)
+  const char* ver = getenv("HFL_ATTN_V");                  // "1": one head per warp, "2": two heads per warp
   const bool two = (H % 2 == 0) && !(ver && ver[0] == '1');
+  const Win3Smem lay3 = win3_layout(H, K, hat, bnd);
+  if (H % 8 == 0 && lay3.total <= 227 * 1024 && !(ver && (ver[0] == '1' || ver[0] == '2'))) {
+    // v3: pair bias summed once per 8 heads (see k_window_attn3)
+    const int smem3 = lay3.total;
+    int grid3 = (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
+#define HFL_WA3_CASE(NT_)                                                                         \
+  case NT_: {                                                                                     \
+    static int smem_set3 = 0;                                                                     \
+    if (smem3 > smem_set3) {                                                                      \
+      HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
+      smem_set3 = smem3;                                                                          \
+    }                                                                                             \
+    HFL_LAUNCH((k_window_attn3<NT_><<<grid3, 256, smem3, st>>>(p)));                              \
+    return HFL_OK;                                                                                \
+  }
+    switch (NT) {
+      HFL_WA3_CASE(2) HFL_WA3_CASE(3) HFL_WA3_CASE(4) HFL_WA3_CASE(5) HFL_WA3_CASE(6) HFL_WA3_CASE(7)
+      HFL_WA3_CASE(8) HFL_WA3_CASE(9) HFL_WA3_CASE(10)
+      default: return fail(HFL_ERR_UNSUPPORTED, "unsupported window size%s (%lld)", "", (long long)K);
+    }
+#undef HFL_WA3_CASE
+  }
   const int smem = two ? ((H / 2 * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + NTC * 8 +
                              H * NTC * 4 + H * 2 * NTC * AT_ROW
                        : ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + 2 * NTC * 8 +
