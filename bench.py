@@ -274,8 +274,8 @@ def run_native(args, rank, world, device):
         return
     ms, launches = timed(step_resident, args.steps, args.warmup)
     sampler.stop_flag = True
-    ms_e2e, _ = timed(step_e2e, max(2, args.steps // 2), 1, drain=drain_e2e)
-    e2e_steps = max(2, args.steps // 2)
+    e2e_steps = max(2, args.steps)
+    ms_e2e, _ = timed(step_e2e, e2e_steps, max(3, args.warmup), drain=drain_e2e)
     if rank != 0:
         return
     value = world * B * args.steps / (ms / 1e3)

@@ -861,6 +861,10 @@ __global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) 
         const uint8_t* sV = sK + NTC * AT_ROW;
         float q[AT_HD];
         {
+          // keep the unpacking of the prefetched row HERE: without the (empty) volatile asm the compiler
+          // hoists it to right behind the loads and the warp waits for them before the bias build
+          asm volatile("" : "+r"(qrt0.x), "+r"(qrt0.y), "+r"(qrt0.z), "+r"(qrt0.w),
+                            "+r"(qrt1.x), "+r"(qrt1.y), "+r"(qrt1.z), "+r"(qrt1.w));
           const uint4 a = qrt0, b = qrt1;
           const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
