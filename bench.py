@@ -397,6 +397,7 @@ def main():
                     help='profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop and exit '
                          '(use with ncu --profile-from-start off); prints no bench line')
     args = ap.parse_args()
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # NCCL's version banner must not land on stdout
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))

@@ -106,14 +106,23 @@ __device__ __forceinline__ void load_planar(const float* base, int lane, float (
 template <int V>
 __device__ __forceinline__ void warp_ln_planar(float (&v)[V], const float* g, const float* b, int lane,
                                                float eps) {
-  float s = 0.f;
+  // One reduction round for both moments (the two butterfly chains interleave): the CPE kernel is
+  // bound by the latency of its per-row dependency chain, of which the four serial warp reductions of
+  // the two-pass form were a quarter.  Sums are taken relative to this lane-0 element (shifted
+  // moments), so the variance does not cancel when |mean| >> std.
+  const float shift = __shfl_sync(0xffffffffu, v[0], 0);
+  float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int j = 0; j < V; ++j) s += v[j];
-  const float mean = warp_sum(s) / (32.f * V);
-  float q = 0.f;
+  for (int j = 0; j < V; ++j) { const float d = v[j] - shift; s += d; q = fmaf(d, d, q); }
 #pragma unroll
-  for (int j = 0; j < V; ++j) { float d = v[j] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) / (32.f * V) + eps);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float inv_n = 1.f / (32.f * V);
+  const float ms = s * inv_n;
+  const float mean = shift + ms;
+  const float rstd = rsqrtf(fmaxf(q * inv_n - ms * ms, 0.f) + eps);
   float gg[V], bb[V];
   load_planar<V>(g, lane, gg);
   load_planar<V>(b, lane, bb);

@@ -155,11 +155,31 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
     rank, world = _dist_info()
     spans = shard_batches(len(keys), params.val_batch_size, rank, world)
     chunks = []
-    for _, b, e in spans:
-        clouds = [prepare_cloud(pc_loader(os.path.join(params.dataset_folder,
-                                                       data_set[k]['query'])), params, normalize, cyl)
-                  for k in keys[b:e]]
-        chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
+
+    def load(k):
+        return prepare_cloud(pc_loader(os.path.join(params.dataset_folder, data_set[k]['query'])),
+                             params, normalize, cyl)
+
+    # The reference reads and prepares every submap serially in the main process, in line with the
+    # GPU work (eval/pnv_evaluate.py:155-176).  Here the files of the NEXT batches are read and
+    # prepared by a small thread pool (numpy / torch release the GIL) while the GPU embeds the
+    # current one; results are consumed strictly in dataset order, so batch composition is unchanged.
+    workers = int(os.environ.get('HFL_LOADER_THREADS', min(16, os.cpu_count() or 1)))
+    if workers <= 1 or not spans:
+        for _, b, e in spans:
+            clouds = [load(k) for k in keys[b:e]]
+            chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            ahead = 2                                            # batches in flight on the host side
+            pending = [[pool.submit(load, k) for k in keys[b:e]] for _, b, e in spans[:ahead]]
+            for t in range(len(spans)):
+                clouds = [f.result() for f in pending.pop(0)]
+                if t + ahead < len(spans):
+                    _, b, e = spans[t + ahead]
+                    pending.append([pool.submit(load, k) for k in keys[b:e]])
+                chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
     dim = params.model_params.output_dim
     local = torch.cat(chunks) if chunks else torch.zeros((0, dim), device=device)
     return gather_rows(local, spans, len(keys), rank, world).cpu().numpy()

@@ -89,3 +89,11 @@ def test_evaluate_end_to_end_vs_oracle(tmp_path):
     assert abs(stats['oxford']['ave_recall'][0] - 0.5 * (rec_o[0] + rec_o2[0])) < 0.1
     E.pnv_write_eval_stats(os.path.join(root, 'res.txt'), 'prefix', stats)
     assert 'AR@1' in open(os.path.join(root, 'res.txt')).read()
+    # the per-split report (eval/pnv_evaluate_splits.py mirror) runs the same embedding path
+    from hotformerloc_b200.eval import pnv_evaluate_splits as S
+    st = S.evaluate(model, 'cuda', params)
+    assert set(st) == set(stats) and 'average' in st['oxford']
+    assert abs(st['oxford']['average']['ave_recall'][0] - stats['oxford']['ave_recall'][0]) < 1e-9
+    assert abs(st['average']['average']['ave_one_percent_recall'] - stats['average']['ave_one_percent_recall']) < 1e-9
+    S.pnv_write_eval_stats(os.path.join(root, 'res_splits.txt'), 'prefix', st)
+    assert 'Split: [' in open(os.path.join(root, 'res_splits.txt')).read()
