@@ -391,7 +391,7 @@ def main():
     ap.add_argument('--config', default='oxford')
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--points', type=int, default=4096)
-    ap.add_argument('--cpu-sample', type=int, default=4)
+    ap.add_argument('--cpu-sample', type=int, default=8)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop and exit '
