@@ -644,11 +644,14 @@ __host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd) 
   return m;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) {
+// WPH = warps per head: 1 -> 8 warps, two windows per SM; 2 -> 16 warps sharing a head's query tiles,
+// for windows whose tables allow only one CTA per SM (K = 64: 123 KB)
+template <int NT, int WPH>
+__global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAttnParams p) {
   constexpr int NTC = NT * 8;
   extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int warp_id = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int warp = warp_id & 7, part = warp_id >> 3;         // head within the pass, share of its query tiles
   const int g = lane >> 2, t = lane & 3;
   const int K = p.K, hat = p.hat, L = K + hat;
   const int num = 2 * p.bnd + 1, sub = num + 2;
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) 
         const int piece = threadIdx.x & 15;
         const __nv_bfloat16* src0 = p.qkv + p.C + ps * 128 + piece * 8;
         const uint32_t dst0 = kv_u + (uint32_t)(piece >> 1) * (2 * NTC * AT_ROW);
-        for (int r = threadIdx.x >> 4; r < 2 * NTC; r += 16) {
+        for (int r = threadIdx.x >> 4; r < 2 * NTC; r += 16 * WPH) {
           const int which = r >= NTC, sl = r - which * NTC;            // 0 = K, 1 = V
           const bool ok = sl < L;
           const int64_t row = ok ? row_base + (int64_t)sl * row_step : 0;
@@ -739,10 +742,10 @@ __global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) 
         qf[0] = __ldg(q0 + t); qf[2] = __ldg(q0 + t + 4);
         qf[1] = __ldg(q1 + t); qf[3] = __ldg(q1 + t + 4);
       };
-      uint32_t qn[4];
-      load_q(0, qn);
+      uint32_t qn[4] = {0u, 0u, 0u, 0u};
+      if (part < n_mt) load_q(part, qn);
       uint4 qrt0 = make_uint4(0u, 0u, 0u, 0u), qrt1 = qrt0;
-      if (hat) {
+      if (hat && part == 0) {
         const uint4* qp = reinterpret_cast<const uint4*>(qh + row_base * C3);
         qrt0 = __ldg(qp);
         qrt1 = __ldg(qp + 1);
@@ -755,7 +758,7 @@ __global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) 
       // ---- bias of every (query, key) pair for the 8 heads of this pass, in fragment order ----
       {
         const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_rpe + ps * 3 * sub);
-        for (int tile = warp; tile < n_mt * NT; tile += 8) {
+        for (int tile = warp_id; tile < n_mt * NT; tile += 8 * WPH) {
           const int mt = tile / NT, nt = tile - mt * NT;
           const short4 ti[2] = {s_tok[mt * 16 + g + hat], s_tok[mt * 16 + g + 8 + hat]};
           const int c0 = nt * 8 + 2 * t;
@@ -799,11 +802,11 @@ __global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) 
       const uint32_t sV_u = sK_u + NTC * AT_ROW;
       const uint8_t* sK = smem + lay.kv + (size_t)warp * (2 * NTC * AT_ROW);
       const uint2* bias_h = s_bias + (size_t)warp * n_mt * NT * 32 + lane;
-      for (int mt = 0; mt < n_mt; ++mt) {
+      for (int mt = part; mt < n_mt; mt += WPH) {
         const int64_t row0 = row_base + (int64_t)(mt * 16 + g + hat) * row_step;
         const int64_t row1 = row0 + 8 * (int64_t)row_step;
         uint32_t qa[4] = {qn[0], qn[1], qn[2], qn[3]};
-        if (mt + 1 < n_mt) load_q(mt + 1, qn);       // next tile's Q in flight during this tile
+        if (mt + WPH < n_mt) load_q(mt + WPH, qn);   // next tile's Q in flight during this tile
         float s[NT][4];
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -856,7 +859,7 @@ __global__ void __launch_bounds__(256, 2) k_window_attn3(const WinAttnParams p) 
         d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
       }
       // ---- the relay-token query row of this head (no RPE): lanes over keys, then over (dim, half) ----
-      if (hat) {
+      if (hat && part == 0) {
         const int64_t rowq = row_base;
         const uint8_t* sV = sK + NTC * AT_ROW;
         float q[AT_HD];
@@ -1108,15 +1111,27 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   if (H % 8 == 0 && lay3.total <= 227 * 1024 && !(ver && (ver[0] == '1' || ver[0] == '2'))) {
     // v3: pair bias summed once per 8 heads (see k_window_attn3)
     const int smem3 = lay3.total;
-    int grid3 = (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
+    // one CTA per SM only (tables > half of the shared memory): 16 warps per window instead of 8
+    const char* w2 = getenv("HFL_ATTN_WPH");
+    const bool wph2 = w2 ? w2[0] == '2' : (2 * smem3 + 2048 > 227 * 1024 && K >= 32);
+    int grid3 = wph2 ? (int)(n_win < kSMs ? n_win : kSMs) : (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
 #define HFL_WA3_CASE(NT_)                                                                         \
   case NT_: {                                                                                     \
+    if (wph2) {                                                                                   \
+      static int smem_set3b = 0;                                                                  \
+      if (smem3 > smem_set3b) {                                                                   \
+        HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
+        smem_set3b = smem3;                                                                       \
+      }                                                                                           \
+      HFL_LAUNCH((k_window_attn3<NT_, 2><<<grid3, 512, smem3, st>>>(p)));                         \
+      return HFL_OK;                                                                              \
+    }                                                                                             \
     static int smem_set3 = 0;                                                                     \
     if (smem3 > smem_set3) {                                                                      \
-      HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
+      HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
       smem_set3 = smem3;                                                                          \
     }                                                                                             \
-    HFL_LAUNCH((k_window_attn3<NT_><<<grid3, 256, smem3, st>>>(p)));                              \
+    HFL_LAUNCH((k_window_attn3<NT_, 1><<<grid3, 256, smem3, st>>>(p)));                           \
     return HFL_OK;                                                                                \
   }
     switch (NT) {

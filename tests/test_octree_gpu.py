@@ -67,7 +67,8 @@ def test_reference_fixtures(golden_dir):
     assert np.array_equal(torch.cat(o.neighs[1:]).cpu().numpy(), fx['b45_neigh'])
 
 
-@pytest.mark.parametrize('depth,n,B', [(9, 4096, 1), (9, 4096, 5), (7, 30000, 3), (6, 777, 4)])
+@pytest.mark.parametrize('depth,n,B', [(9, 4096, 1), (9, 4096, 5), (7, 30000, 3), (6, 777, 4),
+                                       (9, 65536, 2), (9, 262144, 1)])   # configs[4] point-count sweep sizes
 def test_lidar_clouds(depth, n, B):
     g = torch.Generator().manual_seed(11)
     _check_against_oracle([M.lidar_cloud(n, g) for _ in range(B)], depth)
