@@ -20,6 +20,7 @@
 // (thread-local: one thread owns one row of TMEM), ReLU, fp32 and/or bf16 stores with an
 // optional output row map (relay-token rows / hierarchical window layout).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -50,6 +51,7 @@ struct GemmParams {
   int M, N, KD, Cin;        // Ktot = KD * Cin
   int block_n, n_tiles;
   int ws;                   // weight-stationary mode
+  int dense;                // idx == NULL, KD == 1: A tiles are plain 2-D boxes, loaded by TMA (tmap_a)
   // epilogue
   const float* bias;        // [N] or NULL
   const float* res;         // fp32 residual, row-mapped like out_v, or NULL
@@ -176,7 +178,8 @@ __device__ __forceinline__ void res_add(uint32_t stage, int lane, const uint4 (&
 
 template <bool WS>
 __global__ void __launch_bounds__(G_THREADS, 1)
-k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+              const GemmParams p) {
   constexpr int G_STAGES = WS ? G_STAGES_WS : G_STAGES_STREAM;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = ptx::smem_u32(smem_raw);
@@ -210,7 +213,9 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) {
-      ptx::mbar_init(bar_full + 8 * s, WS ? G_PROD_THREADS : G_PROD_THREADS + 1);
+      // arrivals per stage: the producers' cp.async groups (+ the weight TMA's expect-tx in stream
+      // mode); dense mode: only the TMA issuer's expect-tx (A box, and the W box in stream mode)
+      ptx::mbar_init(bar_full + 8 * s, p.dense ? 1 : (WS ? G_PROD_THREADS : G_PROD_THREADS + 1));
       ptx::mbar_init(bar_empty + 8 * s, 1);
     }
     ptx::mbar_init(bar_w, 1);
@@ -235,6 +240,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     // on the critical path of the A gather (stream-mode convs run at ~0.5 us per K block).
     if (lane < G_TMA_ISSUERS) {
       ptx::prefetch_tmap(&tmap_w);
+      if (p.dense) ptx::prefetch_tmap(&tmap_a);
       const uint32_t b_bytes = (uint32_t)BN * G_BK * 2;
       if (WS) {
         if (lane == 0) {                                   // resident W tile: one shot
@@ -242,16 +248,32 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
           for (int kb = 0; kb < k_blocks; ++kb)
             ptx::tma_load_2d(sB + kb * b_bytes, &tmap_w, bar_w, kb * G_BK, ws_n_blk * BN);
         }
+        if (p.dense) {
+          // dense Linear: the 128 x 64 A box of every K block comes by TMA as well (rows >= M are
+          // zero-filled by the tensor map); the cp.async producer warps stay idle
+          uint32_t g = 0;
+          for (int t = t_begin; t < t_end; t += t_step) {
+            for (int kb = 0; kb < k_blocks; ++kb, ++g) {
+              if ((int)(g % G_TMA_ISSUERS) != lane) continue;
+              const uint32_t s = g % G_STAGES, ph = (g / G_STAGES) & 1;
+              ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+              ptx::mbar_arrive_expect_tx(bar_full + 8 * s, G_A_BYTES);
+              ptx::tma_load_2d(sA + s * G_A_BYTES, &tmap_a, bar_full + 8 * s, kb * G_BK, t * G_BM);
+            }
+          }
+        }
       } else {
         uint32_t g = 0;
         for (int t = t_begin; t < t_end; t += t_step) {
-          const int n_blk = t % p.n_tiles;
+          const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
           for (int kb = 0; kb < k_blocks; ++kb, ++g) {
             if ((int)(g % G_TMA_ISSUERS) != lane) continue;
             const uint32_t s = g % G_STAGES, ph = (g / G_STAGES) & 1;
             ptx::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * s, p.dense ? b_bytes + G_A_BYTES : b_bytes);
             ptx::tma_load_2d(sB + s * G_B_BYTES, &tmap_w, bar_full + 8 * s, kb * G_BK, n_blk * BN);
+            if (p.dense)
+              ptx::tma_load_2d(sA + s * G_A_BYTES, &tmap_a, bar_full + 8 * s, kb * G_BK, m_blk * G_BM);
           }
         }
       }
@@ -265,7 +287,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     const int pt = (warp - G_W_PROD) * 32 + lane;
     const int c = pt & 7, rbase = pt >> 3;
     uint32_t g = 0;                                      // k-block counter (ring position)
-    for (int t = t_begin; t < t_end; t += t_step) {
+    for (int t = t_begin; t < (p.dense ? t_begin : t_end); t += t_step) {
       const int m_blk = WS ? t : t / p.n_tiles, n_blk = WS ? ws_n_blk : t % p.n_tiles;
       const int m0 = m_blk * G_BM + rbase;
       for (int kb = 0; kb < k_blocks; ++kb, ++g) {
@@ -510,7 +532,20 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "cuTensorMapEncodeTiled failed%s (%lld)", "", (long long)cr);
+  // dense Linear (no gather): A tiles are 2-D boxes of the row-major [M, Cin] matrix -> TMA
+  const int dense = (idx == nullptr && KD == 1 && !(getenv("HFL_GEMM_DENSE_TMA") && getenv("HFL_GEMM_DENSE_TMA")[0] == '0'));
+  CUtensorMap tmap_a = tmap;
+  if (dense) {
+    cuuint64_t adims[2] = {(cuuint64_t)Cin, (cuuint64_t)M};
+    cuuint64_t astr[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t abox[2] = {(cuuint32_t)G_BK, (cuuint32_t)G_BM};
+    cr = enc(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A), adims, astr, abox, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "cuTensorMapEncodeTiled (A) failed%s (%lld)", "", (long long)cr);
+  }
   GemmParams p;
+  p.dense = dense;
   p.A = (const __nv_bfloat16*)A; p.idx = idx; p.M = (int)M; p.N = N; p.KD = KD; p.Cin = Cin;
   p.block_n = block_n; p.n_tiles = n_tiles; p.bias = bias; p.res = res; p.act = act;
   p.out_v_f32 = out_v_f32; p.out_v_bf16 = (__nv_bfloat16*)out_v_bf16; p.ln_g = ln_g; p.ln_b = ln_b;
@@ -527,11 +562,11 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
   p.ws = ((int64_t)Ktot * block_n * 2 <= G_WS_W_BYTES) && (m_tiles * n_tiles >= 2 * kSMs);
   if (p.ws) {
     const int grid = (kSMs / n_tiles) * n_tiles;
-    HFL_LAUNCH((k_gather_gemm<true><<<grid, G_THREADS, G_SMEM, st>>>(tmap, p)));
+    HFL_LAUNCH((k_gather_gemm<true><<<grid, G_THREADS, G_SMEM, st>>>(tmap, tmap_a, p)));
   } else {
     const int64_t tiles = m_tiles * n_tiles;
     const int grid = (int)(tiles < kSMs ? tiles : kSMs);
-    HFL_LAUNCH((k_gather_gemm<false><<<grid, G_THREADS, G_SMEM, st>>>(tmap, p)));
+    HFL_LAUNCH((k_gather_gemm<false><<<grid, G_THREADS, G_SMEM, st>>>(tmap, tmap_a, p)));
   }
   return HFL_OK;
 }
