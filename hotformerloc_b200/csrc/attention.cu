@@ -802,6 +802,13 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
       const uint32_t sV_u = sK_u + NTC * AT_ROW;
       const uint8_t* sK = smem + lay.kv + (size_t)warp * (2 * NTC * AT_ROW);
       const uint2* bias_h = s_bias + (size_t)warp * n_mt * NT * 32 + lane;
+      // this head's K fragments are the same for every query tile: keep them in registers
+      uint32_t kf[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        kf[nt][0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
+        kf[nt][1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
+      }
       for (int mt = part; mt < n_mt; mt += WPH) {
         const int64_t row0 = row_base + (int64_t)(mt * 16 + g + hat) * row_step;
         const int64_t row1 = row0 + 8 * (int64_t)row_step;
@@ -814,10 +821,7 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
           const uint2 bb = bias_h[(mt * NT + nt) * 32];
           s[nt][0] = h_lo(bb.x); s[nt][1] = h_hi(bb.x);
           s[nt][2] = h_lo(bb.y); s[nt][3] = h_hi(bb.y);
-          uint32_t kb[2];
-          kb[0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
-          kb[1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
-          ptx::mma16816(s[nt], qa, kb);
+          ptx::mma16816(s[nt], qa, kf[nt]);
           mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
           mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
         }
