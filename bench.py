@@ -334,7 +334,19 @@ def run_native(args, rank, world, device):
         'gpu_launches': int(launches), 'clocks': sampler.summary(), 'roofline': roof, 'roofline_by_kernel': roof_all,
         'kernel_time_shares': shares, 'cpu_baseline': cpu,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def cpu_baseline(args, sample=4, steps=1, warmup=0):
@@ -379,7 +391,7 @@ def run_reference(args, rank, world):
            'cpu_baseline': cpu,
            'e2e': {'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
                    'd2h_bytes_per_step': 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -397,7 +409,12 @@ def main():
                     help='profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop and exit '
                          '(use with ncu --profile-from-start off); prints no bench line')
     args = ap.parse_args()
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # NCCL's version banner must not land on stdout
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner
+    # at NCCL_DEBUG=VERSION, for one) is sent to stderr; emit() writes to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
