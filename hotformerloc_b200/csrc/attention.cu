@@ -735,15 +735,20 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
       // requested now, so that their latency hides behind the bias build
       const int h = ps * 8 + warp;
       const __nv_bfloat16* qh = p.qkv + h * AT_HD;
-      auto load_q = [&](int mt, uint32_t (&qf)[4]) {
-        const int64_t r0_ = row_base + (int64_t)(mt * 16 + g + hat) * row_step;
-        const uint32_t* q0 = reinterpret_cast<const uint32_t*>(qh + r0_ * C3);
-        const uint32_t* q1 = reinterpret_cast<const uint32_t*>(qh + (r0_ + 8 * (int64_t)row_step) * C3);
-        qf[0] = __ldg(q0 + t); qf[2] = __ldg(q0 + t + 4);
-        qf[1] = __ldg(q1 + t); qf[3] = __ldg(q1 + t + 4);
+      // Q / output rows of this warp's query tiles advance by a constant stride: running pointers
+      // (the 64-bit row arithmetic per tile was ~10 % of the head loop's instructions)
+      const int64_t qrow0 = row_base + (int64_t)(part * 16 + g + hat) * row_step;
+      const uint32_t* qp0 = reinterpret_cast<const uint32_t*>(qh + qrow0 * C3) + t;
+      const size_t q_half = (size_t)4 * row_step * C3, q_tile = (size_t)8 * WPH * row_step * C3;   // in 32-bit words
+      uint32_t* op0 = reinterpret_cast<uint32_t*>(p.out + qrow0 * p.C + h * AT_HD) + t;
+      const size_t o_half = (size_t)4 * row_step * p.C, o_tile = (size_t)8 * WPH * row_step * p.C;
+      auto load_q = [&](uint32_t (&qf)[4]) {
+        qf[0] = __ldg(qp0); qf[2] = __ldg(qp0 + 4);
+        qf[1] = __ldg(qp0 + q_half); qf[3] = __ldg(qp0 + q_half + 4);
+        qp0 += q_tile;
       };
       uint32_t qn[4] = {0u, 0u, 0u, 0u};
-      if (part < n_mt) load_q(part, qn);
+      if (part < n_mt) load_q(qn);
       uint4 qrt0 = make_uint4(0u, 0u, 0u, 0u), qrt1 = qrt0;
       if (hat && part == 0) {
         const uint4* qp = reinterpret_cast<const uint4*>(qh + row_base * C3);
@@ -810,10 +815,8 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
         kf[nt][1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
       }
       for (int mt = part; mt < n_mt; mt += WPH) {
-        const int64_t row0 = row_base + (int64_t)(mt * 16 + g + hat) * row_step;
-        const int64_t row1 = row0 + 8 * (int64_t)row_step;
         uint32_t qa[4] = {qn[0], qn[1], qn[2], qn[3]};
-        if (mt + WPH < n_mt) load_q(mt + WPH, qn);   // next tile's Q in flight during this tile
+        if (mt + WPH < n_mt) load_q(qn);             // next tile's Q in flight during this tile
         float s[NT][4];
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -855,12 +858,11 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
           ptx::mma16816(ls, pa, ones);
         }
         const float i0 = 1.f / ls[0], i1 = 1.f / ls[2];
-        uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
-        uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
-        d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
-        d0[t + 4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
-        d1[t] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
-        d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
+        op0[0] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
+        op0[4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
+        op0[o_half] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
+        op0[o_half + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
+        op0 += o_tile;
       }
       // ---- the relay-token query row of this head (no RPE): lanes over keys, then over (dim, half) ----
       if (hat && part == 0) {
