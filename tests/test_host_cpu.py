@@ -223,3 +223,35 @@ def test_evaluate_splits_bookkeeping(tmp_path, monkeypatch):
     txt = open(out).read()
     assert 'Split: [split0]' in txt and '[average]' in txt and 'AR@1%' in txt
     S.print_eval_stats(stats)
+
+
+def test_config4_dataset_roundtrip(tmp_path):
+    """tools/config4_eval.py writes the reference's on-disk evaluation format (binary .pcd submaps +
+    per-run dicts with 'query' / 'northing' / 'easting' / true-neighbour lists); the
+    native PCD reader and prepare_cloud (Normalize -> range mask -> cylindrical) consume it."""
+    import importlib.util
+    from hotformerloc_b200.config.presets import write_configs
+    from hotformerloc_b200.datasets.CSWildPlaces.CSWildPlaces_raw import CSWildPlacesPointCloudLoader
+    from hotformerloc_b200.datasets.coordinate_utils import CylindricalCoordinates, Normalize
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    from hotformerloc_b200.misc.utils import TrainingParams
+    spec = importlib.util.spec_from_file_location('config4_eval', os.path.join(ROOT, 'tools', 'config4_eval.py'))
+    c4 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c4)
+    sets = c4.make_dataset(str(tmp_path), runs=2, per_run=3, points=2000, seed=3)
+    assert len(sets) == 2 and sorted(sets[0]) == [0, 1, 2]
+    assert sets[0][1][1] == [1] and sets[0][1][0] == []           # true neighbour in the OTHER run only
+    loader = CSWildPlacesPointCloudLoader()
+    pts = loader(os.path.join(tmp_path, sets[1][2]['query']))
+    assert pts.dtype == np.float32 and pts.shape[1] == 3 and 1500 < len(pts) <= 2000
+    assert np.isfinite(pts).all() and np.abs(pts).max() <= 31.0   # metres
+    paths = write_configs(os.path.join(tmp_path, 'cfg'), 'wild-places', dataset_folder=str(tmp_path))
+    params = TrainingParams(paths['config'], paths['model_config'])
+    out = E.prepare_cloud(pts, params, Normalize(scale_factor=params.scale_factor,
+                                                 unit_sphere_norm=params.unit_sphere_norm),
+                          CylindricalCoordinates(use_octree=True))
+    assert out.dtype == np.float32 and out.shape[1] == 3 and len(out) > 1000
+    assert np.abs(out).max() <= 1.0
+    # batches of val_batch_size in dataset order, round-robin over the ranks (SURVEY.md 8e)
+    spans = [E.shard_batches(300, 128, r, 2) for r in range(2)]
+    assert spans[0] == [(0, 0, 128), (2, 256, 300)] and spans[1] == [(1, 128, 256)]
