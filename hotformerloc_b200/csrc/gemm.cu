@@ -52,6 +52,7 @@ struct GemmParams {
   int block_n, n_tiles;
   int ws;                   // weight-stationary mode
   int dense;                // idx == NULL, KD == 1: A tiles are plain 2-D boxes, loaded by TMA (tmap_a)
+  int plain2;               // two-chunk fast path for the +bias / bf16-store epilogue (HFL_GEMM_PLAIN2=0 disables)
   // epilogue
   const float* bias;        // [N] or NULL
   const float* res;         // fp32 residual, row-mapped like out_v, or NULL
@@ -360,6 +361,8 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
     float* v_b = v_bias + 256;
     const bool do_ln = p.ln_g != nullptr;
     const bool has_res = p.res != nullptr;
+    const bool plain_bf16 = WS && !has_res && !do_ln && p.act != 1 && p.out_v_f32 == nullptr && p.out_v_bf16 != nullptr &&
+                            p.plain2;
     int loaded_n0 = -1;
     uint32_t it = 0;
     for (int t = t_begin; t < t_end; t += t_step, ++it) {
@@ -386,6 +389,31 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + cbeg;
       float shift = 0.f, s1 = 0.f, s2 = 0.f;              // shifted sums for LayerNorm
       uint32_t rawA[32];
+      if (plain_bf16) {
+        // qkv-type epilogue (+bias, bf16 store): the tensor-memory load of the NEXT chunk is issued as
+        // soon as this chunk is packed, so its latency hides behind the transpose / store chain
+        auto pack_chunk = [&](const uint32_t (&raw)[32], int col, uint32_t (&w)[16]) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(v_bias + col + 4 * q);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(raw[4 * q]) + bq.x,
+                                                      __uint_as_float(raw[4 * q + 1]) + bq.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(raw[4 * q + 2]) + bq.z,
+                                                      __uint_as_float(raw[4 * q + 3]) + bq.w);
+            w[2 * q] = *reinterpret_cast<uint32_t*>(&h0);
+            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+        };
+        char* gb = reinterpret_cast<char*>(p.out_v_bf16);
+        ptx::tmem_ld32(taddr, rawA);
+        for (int c0 = 0; c0 < HB; c0 += 32) {
+          ptx::tmem_ld_wait();
+          uint32_t w[16];
+          pack_chunk(rawA, c0, w);
+          if (c0 + 32 < HB) ptx::tmem_ld32(taddr + c0 + 32, rawA);
+          store_unit(stage, lane, w, gb, orow, (size_t)p.N * 2, (size_t)(n0 + cbeg + c0) * 2);
+        }
+      } else
       for (int c0 = 0; c0 < HB; c0 += 32) {
         {
           const int cc = c0;
@@ -546,6 +574,7 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
   }
   GemmParams p;
   p.dense = dense;
+  { const char* e = getenv("HFL_GEMM_PLAIN2"); p.plain2 = !(e && e[0] == '0'); }
   p.A = (const __nv_bfloat16*)A; p.idx = idx; p.M = (int)M; p.N = N; p.KD = KD; p.Cin = Cin;
   p.block_n = block_n; p.n_tiles = n_tiles; p.bias = bias; p.res = res; p.act = act;
   p.out_v_f32 = out_v_f32; p.out_v_bf16 = (__nv_bfloat16*)out_v_bf16; p.ln_g = ln_g; p.ln_b = ln_b;
