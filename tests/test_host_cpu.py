@@ -255,3 +255,40 @@ def test_config4_dataset_roundtrip(tmp_path):
     # batches of val_batch_size in dataset order, round-robin over the ranks
     spans = [E.shard_batches(300, 128, r, 2) for r in range(2)]
     assert spans[0] == [(0, 0, 128), (2, 256, 300)] and spans[1] == [(1, 128, 256)]
+
+
+def test_prefetching_loader_keeps_order_and_batch_composition(tmp_path, monkeypatch):
+    """get_latent_vectors reads / prepares the next batches on a thread pool while the current one is
+    embedded; the descriptors must still come out in dataset order with the reference's batch
+    composition (chunks of val_batch_size in dict order, eval/pnv_evaluate.py:151-185)."""
+    from types import SimpleNamespace
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    n, bs = 11, 3
+    rng = np.random.default_rng(5)
+    data_set = {}
+    for i in range(n):
+        pts = rng.uniform(-1, 1, (50 + i, 3))
+        pts[:, 0] = np.clip(pts[:, 0] * 0.01 + i / 20.0, -1, 1)          # cloud i is identifiable by its mean x
+        (tmp_path / f'{i}.bin').write_bytes(pts.astype(np.float64).tobytes())
+        data_set[100 + i] = {'query': f'{i}.bin'}
+    batches = []
+    monkeypatch.setattr(E, 'collate_batch', lambda clouds, device, params: clouds)
+
+    def fake_embed(model, clouds):
+        batches.append([round(float(c[:, 0].mean()) * 20) for c in clouds])
+        return torch.tensor([[c[:, 0].mean(), len(c), 0.0, 1.0] for c in clouds], dtype=torch.float32)
+    monkeypatch.setattr(E, 'compute_embedding', fake_embed)
+    params = SimpleNamespace(debug=False, dataset_name='Oxford', normalize_points=False, scale_factor=None,
+                             unit_sphere_norm=False, load_octree=True, val_batch_size=bs,
+                             dataset_folder=str(tmp_path),
+                             model_params=SimpleNamespace(coordinates='cartesian', output_dim=4))
+    model = SimpleNamespace(eval=lambda: None)
+    outs = {}
+    for threads in ('1', '4'):
+        monkeypatch.setenv('HFL_LOADER_THREADS', threads)
+        batches.clear()
+        outs[threads] = E.get_latent_vectors(model, data_set, 'cpu', params)
+        assert batches == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10]]
+    assert np.array_equal(outs['1'], outs['4'])
+    assert np.allclose(outs['4'][:, 0] * 20, np.arange(n), atol=0.05)
+    assert np.array_equal(outs['4'][:, 1], 50 + np.arange(n))
