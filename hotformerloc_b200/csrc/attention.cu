@@ -5,7 +5,9 @@
 // (N_win,K,K) masks or the (N_win,K,K,3) rel-pos tensors of the reference
 // (models/octree.py:193-209, 272-283): the batch mask and the RPE index are computed
 // from a per-token (x,y,z,submap) int16x4 table.
-//   k_window_attn : octree window attention, plain / dilated / hierarchical (+relay token)
+//   k_window_attn3: octree window attention, plain / dilated / hierarchical (+relay token) -- the
+//                   default: pair bias summed once per 8 heads into a fragment-ordered smem table
+//                   (k_window_attn2 / k_window_attn are the earlier designs, HFL_ATTN_V=2 / 1)
 //   k_varlen_attn : relay-token self-attention over ragged per-submap sequences
 // qkv is the bf16 output of the tcgen05 projection GEMM, laid out [row, 3C] as
 // [q | k | v] x [head, 16]  (octformer_backbone.py:71-72).
