@@ -292,3 +292,32 @@ def test_prefetching_loader_keeps_order_and_batch_composition(tmp_path, monkeypa
     assert np.array_equal(outs['1'], outs['4'])
     assert np.allclose(outs['4'][:, 0] * 20, np.arange(n), atol=0.05)
     assert np.array_equal(outs['4'][:, 1], 50 + np.arange(n))
+
+
+def test_get_latent_vectors_edge_cases(tmp_path, monkeypatch):
+    """Empty run, a run smaller than one batch, and the reference's --debug short cut
+    (eval/pnv_evaluate.py:131-133: random vectors of the right shape, no model call)."""
+    from types import SimpleNamespace
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    calls = []
+    monkeypatch.setattr(E, 'collate_batch', lambda clouds, device, params: clouds)
+    monkeypatch.setattr(E, 'compute_embedding',
+                        lambda model, clouds: (calls.append(len(clouds)), torch.zeros(len(clouds), 4))[1])
+    mk = lambda **kw: SimpleNamespace(debug=False, dataset_name='Oxford', normalize_points=False,
+                                      scale_factor=None, unit_sphere_norm=False, load_octree=True,
+                                      val_batch_size=8, dataset_folder=str(tmp_path),
+                                      model_params=SimpleNamespace(coordinates='cartesian', output_dim=4), **kw)
+    model = SimpleNamespace(eval=lambda: None)
+    out = E.get_latent_vectors(model, {}, 'cpu', mk())
+    assert out.shape == (0, 4) and calls == []
+    (tmp_path / 'a.bin').write_bytes(np.zeros((5, 3)).tobytes())
+    out = E.get_latent_vectors(model, {7: {'query': 'a.bin'}}, 'cpu', mk())
+    assert out.shape == (1, 4) and calls == [1]
+    p = mk()
+    p.debug = True
+    out = E.get_latent_vectors(model, {i: {'query': 'missing.bin'} for i in range(3)}, 'cpu', p)
+    assert out.shape == (3, 4) and calls == [1]
+    with pytest.raises(ValueError):
+        bad = mk()
+        bad.dataset_name = 'NoSuchDataset'
+        E.get_latent_vectors(model, {0: {'query': 'a.bin'}}, 'cpu', bad)
