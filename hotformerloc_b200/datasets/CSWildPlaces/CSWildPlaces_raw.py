@@ -36,6 +36,10 @@ def read_pcd_xyz(path: str) -> np.ndarray:
             data = np.loadtxt(f, dtype=np.float64, ndmin=2)
             cols = [names.index(a) for a in ('x', 'y', 'z')]
             xyz = data[:npts, cols]
+        elif mode == 'binary' and names == ['x', 'y', 'z'] and all(ft is np.float32 for ft in fmts):
+            # xyz-only float32 records: one reshape (float32 -> float64 -> float32 below is the identity)
+            xyz = np.frombuffer(f.read(npts * 12), dtype=np.float32, count=npts * 3).reshape(npts, 3)
+            return np.ascontiguousarray(xyz[np.isfinite(xyz).all(1)])
         elif mode == 'binary':
             dt = np.dtype({'names': names, 'formats': fmts})
             rec = np.frombuffer(f.read(npts * dt.itemsize), dtype=dt, count=npts)

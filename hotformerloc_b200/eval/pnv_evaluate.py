@@ -171,15 +171,23 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
             chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
     else:
         from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=workers) as pool:
-            ahead = 2                                            # batches in flight on the host side
-            pending = [[pool.submit(load, k) for k in keys[b:e]] for _, b, e in spans[:ahead]]
-            for t in range(len(spans)):
-                clouds = [f.result() for f in pending.pop(0)]
-                if t + ahead < len(spans):
-                    _, b, e = spans[t + ahead]
-                    pending.append([pool.submit(load, k) for k in keys[b:e]])
-                chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
+        # one intra-op thread per torch CPU op while the pool runs: the per-submap tensors are small
+        # (tens of K points) and N pool threads each fanning out to an OpenMP team oversubscribe the
+        # cores (measured on 8 cores, 8 workers: 485 -> 755 submaps/s)
+        intra = torch.get_num_threads()
+        torch.set_num_threads(1)
+        try:
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                ahead = 2                                        # batches in flight on the host side
+                pending = [[pool.submit(load, k) for k in keys[b:e]] for _, b, e in spans[:ahead]]
+                for t in range(len(spans)):
+                    clouds = [f.result() for f in pending.pop(0)]
+                    if t + ahead < len(spans):
+                        _, b, e = spans[t + ahead]
+                        pending.append([pool.submit(load, k) for k in keys[b:e]])
+                    chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
+        finally:
+            torch.set_num_threads(intra)
     dim = params.model_params.output_dim
     local = torch.cat(chunks) if chunks else torch.zeros((0, dim), device=device)
     return gather_rows(local, spans, len(keys), rank, world).cpu().numpy()

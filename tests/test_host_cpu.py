@@ -68,9 +68,18 @@ def test_loaders(tmp_path):
         f.write(hdr + 'DATA ascii\n')
         for r in rec:
             f.write(' '.join(repr(float(v)) for v in r) + '\n')
+    xyz_hdr = ('VERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 100\nHEIGHT 1\n'
+               'POINTS 100\nDATA binary\n')
+    bad = pts.astype(np.float32).copy()
+    bad[7, 1] = np.nan                                       # non-finite points are dropped (open3d behaviour)
+    with open(tmp_path / 'd.pcd', 'wb') as f:                # xyz-only float32 records: the reshape fast path
+        f.write(xyz_hdr.encode())
+        f.write(bad.tobytes())
     for name in ('b.pcd', 'c.pcd'):
         assert np.array_equal(CSWildPlacesPointCloudLoader()(str(tmp_path / name)),
                               pts.astype(np.float32))
+    assert np.array_equal(CSWildPlacesPointCloudLoader()(str(tmp_path / 'd.pcd')),
+                          np.delete(pts.astype(np.float32), 7, axis=0))
 
 
 def test_cylindrical_matches_reference_golden():
