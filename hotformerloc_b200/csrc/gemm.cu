@@ -177,8 +177,13 @@ __device__ __forceinline__ void res_add(uint32_t stage, int lane, const uint4 (&
   }
 }
 
-template <bool WS>
-__global__ void __launch_bounds__(G_THREADS, 1)
+// D320 (experimental, HFL_GEMM_DENSE320=1, dense GEMMs only): the same kernel without the four cp.async
+// producer warps -- 320 threads (8 epilogue + MMA + TMA), which lifts the per-thread register cap from 128
+// to 168 and lets the residual / LayerNorm epilogue keep the next accumulator chunk and TWO residual chunks
+// in flight.  Not yet measured on a B200 (DESIGN.md, round-2 plan item 2); the default path is unchanged.
+constexpr int G_THREADS_D320 = 320;
+template <bool WS, bool D320 = false>
+__global__ void __launch_bounds__(D320 ? G_THREADS_D320 : G_THREADS, 1)
 k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
               const GemmParams p) {
   constexpr int G_STAGES = WS ? G_STAGES_WS : G_STAGES_STREAM;
@@ -202,6 +207,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       reinterpret_cast<volatile uint32_t*>(smem + (s_tmem - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = D320 ? 9 : G_W_TMA;             // D320: warps 0-7 epilogue, 8 MMA, 9 TMA
   const int m_tiles = (p.M + G_BM - 1) / G_BM;
   const int k_blocks = (p.KD * p.Cin) / G_BK;
   const int BN = p.block_n;
@@ -235,7 +241,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp == G_W_TMA) {
+  if (warp == W_TMA) {
     // ===================== weight TMA issuer =====================
     // Kept off the cp.async producers: the ~340 ns a thread spends per TMA instruction would sit
     // on the critical path of the A gather (stream-mode convs run at ~0.5 us per K block).
@@ -279,7 +285,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
         }
       }
     }
-  } else if (warp >= G_W_PROD) {
+  } else if (!D320 && warp >= G_W_PROD) {
     // ===================== A producers (+ TMA for W) =====================
     // 128 threads; thread = (16-byte chunk c of the 128-byte K-block row, rows rbase + 16 i):
     // 8 consecutive lanes fetch one full 128-byte line -> every cp.async is sector-complete.
@@ -383,7 +389,11 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
       if (m < p.M) orow = p.out_rows ? __ldg(p.out_rows + m) : m;
       const int32_t yrow = p.y_mapped ? orow : (m < p.M ? m : -1);
       uint4 rbuf[8];
+      uint4 rbuf2[D320 ? 8 : 1];                         // D320: a second residual chunk in flight
       if (has_res) res_issue(p.res, orow, p.N, n0 + cbeg, lane, rbuf);   // first residual chunk
+      if constexpr (D320) {
+        if (has_res && HB > 32) res_issue(p.res, orow, p.N, n0 + cbeg + 32, lane, rbuf2);
+      }
       ptx::mbar_wait(bar_tfull + 8 * acc, aph);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256 + cbeg;
@@ -413,12 +423,13 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
           if (c0 + 32 < HB) ptx::tmem_ld32(taddr + c0 + 32, rawA);
           store_unit(stage, lane, w, gb, orow, (size_t)p.N * 2, (size_t)(n0 + cbeg + c0) * 2);
         }
-      } else
+      } else {
+      if constexpr (D320) ptx::tmem_ld32(taddr, rawA);
       for (int c0 = 0; c0 < HB; c0 += 32) {
         {
           const int cc = c0;
           uint32_t (&raw32)[32] = rawA;
-          ptx::tmem_ld32(taddr + cc, raw32);
+          if constexpr (!D320) ptx::tmem_ld32(taddr + cc, raw32);
           ptx::tmem_ld_wait();
           float v[32];
 #pragma unroll
@@ -429,7 +440,20 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             v[4 * q + 2] = __uint_as_float(raw32[4 * q + 2]) + b.z;
             v[4 * q + 3] = __uint_as_float(raw32[4 * q + 3]) + b.w;
           }
-          if (has_res) {
+          if constexpr (D320) {
+            // next accumulator chunk under this chunk's work; residual chunks alternate between the two
+            // buffers, each refilled two chunks ahead as soon as it has been consumed
+            if (cc + 32 < HB) ptx::tmem_ld32(taddr + cc + 32, raw32);
+            if (has_res) {
+              if ((cc >> 5) & 1) {
+                res_add(stage, lane, rbuf2, v);
+                if (cc + 64 < HB) res_issue(p.res, orow, p.N, n0 + cbeg + cc + 64, lane, rbuf2);
+              } else {
+                res_add(stage, lane, rbuf, v);
+                if (cc + 64 < HB) res_issue(p.res, orow, p.N, n0 + cbeg + cc + 64, lane, rbuf);
+              }
+            }
+          } else if (has_res) {
             res_add(stage, lane, rbuf, v);
             if (cc + 32 < HB) res_issue(p.res, orow, p.N, n0 + cbeg + cc + 32, lane, rbuf);
           }
@@ -451,6 +475,7 @@ k_gather_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant_
             ptx::tmem_st32(taddr + cc, wb);
           }
         }
+      }
       }
       if (do_ln) {
         // per-half (mean, M2) -> exchange with the other column half of this row -> full-row stats
@@ -589,7 +614,16 @@ int hfl_gather_gemm(const void* A, const int32_t* idx, const void* W, int64_t M,
   const int64_t m_tiles = ceil_div(M, G_BM);
   // weight-stationary when the W tile fits next to the A ring and every CTA gets >= 2 M tiles
   p.ws = ((int64_t)Ktot * block_n * 2 <= G_WS_W_BYTES) && (m_tiles * n_tiles >= 2 * kSMs);
-  if (p.ws) {
+  const char* d320 = getenv("HFL_GEMM_DENSE320");
+  if (p.ws && dense && d320 && d320[0] == '1') {          // experimental 320-thread dense instantiation
+    static bool attr320 = false;
+    if (!attr320) {
+      HFL_CUDA(cudaFuncSetAttribute(k_gather_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+      attr320 = true;
+    }
+    const int grid = (kSMs / n_tiles) * n_tiles;
+    HFL_LAUNCH((k_gather_gemm<true, true><<<grid, G_THREADS_D320, G_SMEM, st>>>(tmap, tmap_a, p)));
+  } else if (p.ws) {
     const int grid = (kSMs / n_tiles) * n_tiles;
     HFL_LAUNCH((k_gather_gemm<true><<<grid, G_THREADS, G_SMEM, st>>>(tmap, tmap_a, p)));
   } else {
