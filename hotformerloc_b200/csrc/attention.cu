@@ -631,14 +631,16 @@ __device__ __forceinline__ uint4 hadd2_x4(const uint4 a, const uint4 b) {
 struct Win3Smem {            // byte offsets into dynamic shared memory
   int rpe, tok, rtm, prob, bias, kv, total;
 };
-__host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd) {
+// compact (experimental 3-CTAs-per-SM variant): only the current pass's RPE table is resident and the
+// relay-token probabilities reuse the warp's own (finished) bias slice
+__host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd, bool compact = false) {
   const int L = K + hat, NT = (L + 7) / 8, NTC = NT * 8, sub = 2 * bnd + 3, passes = H / 8;
   Win3Smem m;
   int o = 0;
-  m.rpe = o;  o += passes * 3 * sub * 16;
+  m.rpe = o;  o += (compact ? 1 : passes) * 3 * sub * 16;
   m.tok = o;  o += NTC * 8;
   m.rtm = o;  o += (NTC + 15) & ~15;
-  m.prob = o; o += 8 * NTC * 4;
+  m.prob = o; o += compact ? 0 : 8 * NTC * 4;
   o = (o + 15) & ~15;
   m.bias = o; o += 8 * (K / 16) * NT * 256;
   m.kv = o;   o += 8 * 2 * NTC * AT_ROW;
@@ -648,8 +650,12 @@ __host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd) 
 
 // WPH = warps per head: 1 -> 8 warps, two windows per SM; 2 -> 16 warps sharing a head's query tiles,
 // for windows whose tables allow only one CTA per SM (K = 64: 123 KB)
-template <int NT, int WPH>
-__global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAttnParams p) {
+// CPS = CTAs per SM the kernel is compiled for: 3 (experimental, HFL_ATTN_CTAS=3, WPH = 1 only) caps the
+// registers at 80 (no spills at NT = 7) and uses the compact shared-memory layout (74 KB at K = 48, H = 16);
+// compiled but NOT yet measured on a B200 (DESIGN.md round-2 plan item 3)
+template <int NT, int WPH, int CPS = 2>
+__global__ void __launch_bounds__(256 * WPH, WPH == 1 ? CPS : 1) k_window_attn3(const WinAttnParams p) {
+  constexpr bool COMPACT = CPS == 3;
   constexpr int NTC = NT * 8;
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp_id = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -658,7 +664,7 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
   const int K = p.K, hat = p.hat, L = K + hat;
   const int num = 2 * p.bnd + 1, sub = num + 2;
   const int passes = p.H >> 3;
-  const Win3Smem lay = win3_layout(p.H, K, hat, p.bnd);
+  const Win3Smem lay = win3_layout(p.H, K, hat, p.bnd, COMPACT);
   uint4* s_rpe = reinterpret_cast<uint4*>(smem + lay.rpe);                // [passes][3][sub] 8 x fp16
   short4* s_tok = reinterpret_cast<short4*>(smem + lay.tok);              // [NTC]
   uint8_t* s_rtm = smem + lay.rtm;                                        // [NTC] relay-token row mask
@@ -675,21 +681,41 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
   // The summed bias seeds the accumulator of the QK^T MMA (acc = q.k + bias / scale); the softmax scale
   // is applied inside the exponent: p = 2^(sc * acc - sc * max), one FFMA per score.
   const float inv_scale = 1.0f / p.scale;
-  for (int i = threadIdx.x; i < passes * 3 * sub * 4; i += blockDim.x) {
-    const int hp = i & 3, e = i >> 2;                 // head pair within the entry, entry index
-    const int k = e % sub, axis = (e / sub) % 3, ps = e / (3 * sub);
-    float a = 0.f, b = 0.f;
-    if (k < num) {
-      if (p.rpe) {
-        const float* src = p.rpe + (size_t)(axis * num + k) * p.H + ps * 8 + 2 * hp;
-        a = __ldg(src) * inv_scale;
-        b = __ldg(src + 1) * inv_scale;
+  if constexpr (!COMPACT) {
+    for (int i = threadIdx.x; i < passes * 3 * sub * 4; i += blockDim.x) {
+      const int hp = i & 3, e = i >> 2;               // head pair within the entry, entry index
+      const int k = e % sub, axis = (e / sub) % 3, ps = e / (3 * sub);
+      float a = 0.f, b = 0.f;
+      if (k < num) {
+        if (p.rpe) {
+          const float* src = p.rpe + (size_t)(axis * num + k) * p.H + ps * 8 + 2 * hp;
+          a = __ldg(src) * inv_scale;
+          b = __ldg(src + 1) * inv_scale;
+        }
+      } else if (k == num + 1 && axis == 0) {
+        a = b = -INFINITY;
       }
-    } else if (k == num + 1 && axis == 0) {
-      a = b = -INFINITY;
+      reinterpret_cast<uint32_t*>(s_rpe)[i] = pack_h2(a, b);
     }
-    reinterpret_cast<uint32_t*>(s_rpe)[i] = pack_h2(a, b);
   }
+  // compact layout: the table of pass ps only, refilled at the start of every pass
+  auto fill_rpe_pass = [&](int ps) {
+    for (int i = threadIdx.x; i < 3 * sub * 4; i += blockDim.x) {
+      const int hp = i & 3, e = i >> 2;
+      const int k = e % sub, axis = e / sub;
+      float a = 0.f, b = 0.f;
+      if (k < num) {
+        if (p.rpe) {
+          const float* src = p.rpe + (size_t)(axis * num + k) * p.H + ps * 8 + 2 * hp;
+          a = __ldg(src) * inv_scale;
+          b = __ldg(src + 1) * inv_scale;
+        }
+      } else if (k == num + 1 && axis == 0) {
+        a = b = -INFINITY;
+      }
+      reinterpret_cast<uint32_t*>(s_rpe)[i] = pack_h2(a, b);
+    }
+  };
   for (int i = threadIdx.x; i < NTC; i += blockDim.x)
     if (i >= L) s_tok[i] = make_short4(0, 0, 0, -2);
   const int C3 = 3 * p.C;
@@ -757,14 +783,17 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
         qrt0 = __ldg(qp);
         qrt1 = __ldg(qp + 1);
       }
+      if constexpr (COMPACT) fill_rpe_pass(ps);     // this pass's table only (previous pass fully consumed)
       if (ps == 0) {
         ptx::cp_async_wait<1>();                    // tokens landed (K / V still in flight)
         __syncthreads();
         for (int j = threadIdx.x; j < NTC; j += blockDim.x) s_rtm[j] = s_tok[0].w == s_tok[j].w;
+      } else if constexpr (COMPACT) {
+        __syncthreads();                            // the refilled table is visible to the build
       }
       // ---- bias of every (query, key) pair for the 8 heads of this pass, in fragment order ----
       {
-        const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_rpe + ps * 3 * sub);
+        const uint8_t* tab = reinterpret_cast<const uint8_t*>(s_rpe + (COMPACT ? 0 : ps) * 3 * sub);
         for (int tile = warp_id; tile < n_mt * NT; tile += 8 * WPH) {
           const int mt = tile / NT, nt = tile - mt * NT;
           const short4 ti[2] = {s_tok[mt * 16 + g + hat], s_tok[mt * 16 + g + 8 + hat]};
@@ -909,7 +938,8 @@ __global__ void __launch_bounds__(256 * WPH, 3 - WPH) k_window_attn3(const WinAt
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float l = 0.f;
-        float* pr = s_prob + warp * NTC;
+        // compact: this warp's own bias slice is dead once its query tiles are done (WPH == 1)
+        float* pr = COMPACT ? reinterpret_cast<float*>(s_bias + (size_t)warp * n_mt * NT * 32) : s_prob + warp * NTC;
 #pragma unroll
         for (int u = 0; u < (NTC + 31) / 32; ++u) {
           const int j = lane + 32 * u;
@@ -1118,11 +1148,16 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   const Win3Smem lay3 = win3_layout(H, K, hat, bnd);
   if (H % 8 == 0 && lay3.total <= 227 * 1024 && !(ver && (ver[0] == '1' || ver[0] == '2'))) {
     // v3: pair bias summed once per 8 heads (see k_window_attn3)
-    const int smem3 = lay3.total;
     // one CTA per SM only (tables > half of the shared memory): 16 warps per window instead of 8
     const char* w2 = getenv("HFL_ATTN_WPH");
-    const bool wph2 = w2 ? w2[0] == '2' : (2 * smem3 + 2048 > 227 * 1024 && K >= 32);
-    int grid3 = wph2 ? (int)(n_win < kSMs ? n_win : kSMs) : (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
+    const bool wph2 = w2 ? w2[0] == '2' : (2 * lay3.total + 2048 > 227 * 1024 && K >= 32);
+    // experimental: three windows per SM (compact tables, 80 registers) when they fit
+    const Win3Smem layc = win3_layout(H, K, hat, bnd, true);
+    const char* c3 = getenv("HFL_ATTN_CTAS");
+    const bool cps3 = !wph2 && c3 && c3[0] == '3' && 3 * (layc.total + 1024) <= 227 * 1024;
+    const int smem3 = cps3 ? layc.total : lay3.total;
+    const int per_sm = wph2 ? 1 : (cps3 ? 3 : 2);
+    int grid3 = (int)(n_win < per_sm * kSMs ? n_win : per_sm * kSMs);
 #define HFL_WA3_CASE(NT_)                                                                         \
   case NT_: {                                                                                     \
     if (wph2) {                                                                                   \
@@ -1132,6 +1167,15 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
         smem_set3b = smem3;                                                                       \
       }                                                                                           \
       HFL_LAUNCH((k_window_attn3<NT_, 2><<<grid3, 512, smem3, st>>>(p)));                         \
+      return HFL_OK;                                                                              \
+    }                                                                                             \
+    if (cps3) {                                                                                   \
+      static int smem_set3c = 0;                                                                  \
+      if (smem3 > smem_set3c) {                                                                   \
+        HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
+        smem_set3c = smem3;                                                                       \
+      }                                                                                           \
+      HFL_LAUNCH((k_window_attn3<NT_, 1, 3><<<grid3, 256, smem3, st>>>(p)));                      \
       return HFL_OK;                                                                              \
     }                                                                                             \
     static int smem_set3 = 0;                                                                     \

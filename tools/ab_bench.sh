@@ -4,9 +4,10 @@
 # (submaps/s resident, end to end, ms/step, ms per kernel family).  Toggles of the product path:
 #   HFL_ATTN_V=1|2          window attention: one head per warp | two heads per warp (default: v3, 8 heads per pass)
 #   HFL_ATTN_WPH=1|2        v3: warps per head (default: 2 only when the tables allow one CTA per SM)
+#   HFL_ATTN_CTAS=3         EXPERIMENTAL (kernel tests pass, speed unmeasured): three windows per SM, compact tables, 80 registers
 #   HFL_GEMM_DENSE_TMA=0    dense GEMMs: A by cp.async producers instead of TMA
 #   HFL_GEMM_PLAIN2=0       +bias / bf16-store epilogue without the tensor-memory load prefetch
-#   HFL_GEMM_DENSE320=1     EXPERIMENTAL (not yet run on a GPU): 320-thread dense GEMM instantiation, 168 registers
+#   HFL_GEMM_DENSE320=1     EXPERIMENTAL (kernel tests pass, speed unmeasured): 320-thread dense GEMM instantiation, 168 registers
 #   HFL_FUSED_MLP=""|128|256|128,256   channel widths that use the fused MLP kernel
 #   HFL_LEVEL_STREAMS=1     pyramid levels of an H-OSA block on three streams
 #   HFL_LOADER_THREADS=N    eval file loader threads (1 = serial)
