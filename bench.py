@@ -143,8 +143,14 @@ def kernel_profile(model, octree_fn):
         return {'flop': 4.0 * M * W1.shape[0] * W1.shape[1],
                 'byte': float(M * C * (2 + 4 + 4 + (2 if k.get('out_bf16') is not None else 0)))}
 
+    def proj_mlp_work(O, Wp, bp, g, b, W1, b1, W2, b2, **k):
+        M = k.get('M') or O.shape[0]
+        C = O.shape[1]
+        return {'flop': 2.0 * M * C * C + 4.0 * M * W1.shape[0] * W1.shape[1],
+                'byte': float(M * C * (2 + 4 + 4 + (2 if k.get('out_bf16') is not None else 0)))}
+
     patches = {'gather_gemm': gemm_work, 'window_attn': attn_work, 'cpe_ln': cpe_work,
-               'mlp_fused': mlp_work}
+               'mlp_fused': mlp_work, 'proj_mlp_fused': proj_mlp_work}
     for name, work in patches.items():
         saved[name] = getattr(ops, name)
         setattr(ops, name, wrap(name, saved[name], work))

@@ -39,7 +39,20 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
     HFL_CUDA(cudaPeekAtLastError());                                          \
   } while (0)
 
-constexpr int kSMs = 148;
+constexpr int kSMs = 148;      // B200; grid caps of the small row kernels (any multiple works)
+
+// SM count of the current device (persistent tcgen05 kernels launch one CTA per SM); cached per device.
+inline int sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kSMs;
+  int v = cached[dev].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kSMs;
+    cached[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

@@ -39,6 +39,11 @@ struct MlpParams {
   const int32_t* out_rows;    // [M] or NULL
   int dbg;                    // diagnostics only (HFL_MLP_DBG): 1 no fp32 stores, 2 no bf16 stores, 4 no residual loads
   long long* prof;            // diagnostics only (HFL_MLP_PROF): per-role wait/work cycles of CTA 0
+  // PJ variant (attention output projection + residual + LayerNorm in front of the MLP)
+  const float* bp;            // [C] proj bias
+  const float* ln_g;          // [C] norm2
+  const float* ln_b;
+  float ln_eps;
 };
 
 // GELU (erf form) of two values at once, given h = x / 2 (the epilogue folds the halving into
@@ -124,7 +129,7 @@ __device__ __forceinline__ void ml_res_add(uint32_t stage, int lane, const uint4
   }
 }
 
-template <int C>
+template <int C, bool PJ = false>
 struct MlpSmem {
   static constexpr int KB1 = C / 64;                 // K blocks of GEMM 1
   static constexpr int NCH = 4 * C / ML_CH;          // hidden chunks
@@ -140,18 +145,29 @@ struct MlpSmem {
   static constexpr int OFF_B1 = OFF_ST + ST_BYTES;   // b1 [4C] fp32
   static constexpr int OFF_B2 = OFF_B1 + 4 * C * 4;  // b2 [C] fp32
   static constexpr int OFF_BAR = OFF_B2 + C * 4;
-  static constexpr int TOTAL = OFF_BAR + 256;
+  static constexpr int OFF_PJ = OFF_BAR + 256;       // PJ: proj bias | norm2 gamma | norm2 beta | b2   [4][C] fp32
+  static constexpr int OFF_LNX = OFF_PJ + 4 * C * 4; // PJ: LayerNorm statistics exchange [2 halves][128 rows] float2
+  static constexpr int TOTAL = PJ ? OFF_LNX + 2048 : OFF_BAR + 256;
 };
 
 // cycle accounting for CTA 0 (diagnostics; prof == nullptr in production)
 #define ML_T0() const long long t0_ = PROF ? clock64() : 0
 #define ML_ACC(slot) do { if (PROF) lacc[slot] += clock64() - t0_; } while (0)
 
-template <int C, bool PROF>
+// PJ = true: the attention output projection, its residual add and the block's norm2 run in front of
+// the MLP inside the same CTA (reference: x = x + proj(attn) ; x = x + mlp(norm2(x)),
+// octformer_backbone.py:276-281, hotformerloc_backbone.py:212-216):
+//     acc1 region (C cols)  = o_tile . Wp^T                         GEMM 0, o tile by TMA into the A buffer
+//     epilogue 0: s = acc + bp + residual (+ b2) -> acc2 (fp32, TENSOR MEMORY); LayerNorm(s - b2) -> bf16
+//                 straight into the swizzled A buffer (the MLP operand: no HBM round trip of `y`)
+//     GEMM 1 / epilogue 1 / GEMM 2 as before, GEMM 2 accumulating ON TOP of s
+//     epilogue 2: acc2 -> x (fp32) + bf16 shadow: the residual stream is read once per block here
+template <int C, bool PROF, bool PJ>
 __global__ void __launch_bounds__(ML_THREADS, 1)
 k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+            const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_wp,
             const MlpParams p) {
-  using S = MlpSmem<C>;
+  using S = MlpSmem<C, PJ>;
   constexpr int KB1 = S::KB1, NCH = S::NCH, RING = S::RING, G1S = S::G1S, G2S = S::G2S;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ptx::smem_u32(smem);
@@ -166,6 +182,9 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   const uint32_t h_full = bar + 184;                          // H[2] (aliases acc1): epilogue 1 done
   const uint32_t c2_full = bar + 200, c2_empty = bar + 208;   // acc2
   const uint32_t s_tmem = bar + 216;
+  const uint32_t o_full = bar + 224, c0_full = bar + 232;     // PJ: o tile landed, GEMM 0 done
+  float* s_pj = reinterpret_cast<float*>(smem + S::OFF_PJ);   // PJ: bp | gamma | beta | b2
+  float2* s_lnx = reinterpret_cast<float2*>(smem + S::OFF_LNX);
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 216);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,10 +197,17 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   const long long t_role = PROF ? clock64() : 0;
 
   for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) s_b1[i] = 0.5f * p.b1[i];   // epilogue 1 works on (acc + b1) / 2
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_b2[i] = p.b2[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_b2[i] = PJ ? 0.f : p.b2[i];   // PJ: b2 is folded into epilogue 0
+  if constexpr (PJ) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      s_pj[i] = p.bp[i]; s_pj[C + i] = p.ln_g[i]; s_pj[2 * C + i] = p.ln_b[i]; s_pj[3 * C + i] = p.b2[i];
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
-    for (int k = 0; k < 4; ++k) ptx::mbar_init(a1_full + 8 * k, 128);
+    for (int k = 0; k < 4; ++k) ptx::mbar_init(a1_full + 8 * k, PJ ? 4 : 128);   // PJ: the 4 epilogue warps of the K block's column half
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(c0_full, 1);
     ptx::mbar_init(a1_empty, 1);
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(c1_full + 8 * b, 1); ptx::mbar_init(h_full + 8 * b, 8); }
     ptx::mbar_init(c2_full, 1);
@@ -224,20 +250,43 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       };
       // same order as the MMA issuer: G1(0) G1(1) | G2(j) G1(j+2) ... (G1 runs into the next tile)
       for (int it = 0; it < n_my; ++it) {
-        if (it == 0) { load_w1(0); load_w1(1); }
-        for (int j = 0; j < NCH; ++j) {
-          load_w2(j);
-          if (j + 2 < NCH) load_w1(j + 2);
-          else if (it + 1 < n_my) load_w1(j + 2 - NCH);
+        if constexpr (PJ) {
+          // Wp (K-major [C, C]): C = 256 -> four {64, 256, 1} boxes, C = 128 -> one {64, 128, 2} box
+          if (C == 256) { for (int kb = 0; kb < 4; ++kb) load(&tm_wp, 0, kb); }
+          else load(&tm_wp, 0, 0);
+          load_w1(0); load_w1(1);
+          for (int j = 0; j < NCH; ++j) {
+            load_w2(j);
+            if (j + 2 < NCH) load_w1(j + 2);
+          }
+        } else {
+          if (it == 0) { load_w1(0); load_w1(1); }
+          for (int j = 0; j < NCH; ++j) {
+            load_w2(j);
+            if (j + 2 < NCH) load_w1(j + 2);
+            else if (it + 1 < n_my) load_w1(j + 2 - NCH);
+          }
         }
       }
       if (PROF) lacc[14] = clock64() - t_role;
+    } else if (PJ && lane == ML_ISSUERS) {
+      // o tiles (attention output, the A operand of GEMM 0): four / two 128 x 64 boxes into the A buffer,
+      // as soon as GEMM 1 of the previous tile's last chunk has released it.  Own lane: the weight
+      // issuers never wait on the A buffer.
+      ptx::prefetch_tmap(&tm_o);
+      for (int it = 0; it < n_my; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        ptx::mbar_wait_sleep(a1_empty, (it & 1) ^ 1, 128);
+        ptx::mbar_arrive_expect_tx(o_full, KB1 * ML_STAGE);
+        for (int kb = 0; kb < KB1; ++kb)
+          ptx::tma_load_2d(sA1 + kb * ML_STAGE, &tm_o, o_full, kb * 64, tile * ML_BM);
+      }
     }
   } else if (warp >= 9) {
     // ===================== y-tile producers =====================
     const int pt = (warp - 9) * 32 + lane;
     const int c = pt & 7, rbase = pt >> 3;
-    for (int it = 0; it < n_my; ++it) {
+    for (int it = 0; it < (PJ ? 0 : n_my); ++it) {       // PJ: the A buffer is filled by TMA (o) and by epilogue 0 (y)
       const int tile = blockIdx.x + it * gridDim.x;
       { ML_T0(); ptx::mbar_wait_sleep(a1_empty, (it & 1) ^ 1, 256); ML_ACC(15); }
       const int m0 = tile * ML_BM + rbase;
@@ -305,7 +354,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
           const uint64_t bd = ptx::umma_desc_sw128(sW + s * ML_SLOT + (C == 256 ? 0 : kb * ML_STAGE));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_ts(t_acc2, ta + 8 * k, bd + 2 * k, idesc2, (j | kb | k) != 0);
+            ptx::umma_bf16_ts(t_acc2, ta + 8 * k, bd + 2 * k, idesc2, PJ || (j | kb | k) != 0);   // PJ: acc2 was seeded by epilogue 0
           if (C == 256 || kb == 1) { ptx::umma_commit(w_empty + 8 * s); ++g; }
           ML_ACC(6);
         }
@@ -313,12 +362,43 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       };
       // The tensor pipe executes one thread's MMAs in issue order, so GEMM 1 of chunk q + 2 (which
       // overwrites acc1[q & 1]) is simply issued after GEMM 2 of chunk q (which reads H from it).
+      // GEMM 0 (PJ): acc1 region = o_tile . Wp^T; it may start while epilogue 2 of the previous tile still
+      // reads acc2 (different columns); the H operands it overwrites were consumed by GEMM 2 in issue order
+      auto gemm0 = [&](int t) {
+        const uint32_t idesc0 = ptx::umma_idesc_bf16(ML_BM, C);
+        ptx::mbar_wait(o_full, t & 1);
+        for (int h = 0; h < (C == 256 ? 4 : 1); ++h, ++g) {
+          const uint32_t s = g % RING, ph = (g / RING) & 1;
+          ptx::mbar_wait(w_full + 8 * s, ph);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < (C == 256 ? 1 : 2); ++kk) {
+            const int kb = C == 256 ? h : kk;
+            const uint64_t ad = ptx::umma_desc_sw128(sA1 + kb * ML_STAGE);
+            const uint64_t bd = ptx::umma_desc_sw128(sW + s * ML_SLOT + (C == 256 ? 0 : kk * ML_STAGE));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc0, (kb | k) != 0);
+          }
+          ptx::umma_commit(w_empty + 8 * s);
+        }
+        ptx::umma_commit(c0_full);
+      };
       for (int it = 0; it < n_my; ++it) {
-        if (it == 0) { gemm1(0, 0); gemm1(0, 1); }
-        for (int j = 0; j < NCH; ++j) {
-          gemm2(it, j);
-          if (j + 2 < NCH) gemm1(it, j + 2);
-          else if (it + 1 < n_my) gemm1(it + 1, j + 2 - NCH);
+        if constexpr (PJ) {
+          gemm0(it);
+          gemm1(it, 0); gemm1(it, 1);
+          for (int j = 0; j < NCH; ++j) {
+            gemm2(it, j);
+            if (j + 2 < NCH) gemm1(it, j + 2);
+          }
+        } else {
+          if (it == 0) { gemm1(0, 0); gemm1(0, 1); }
+          for (int j = 0; j < NCH; ++j) {
+            gemm2(it, j);
+            if (j + 2 < NCH) gemm1(it, j + 2);
+            else if (it + 1 < n_my) gemm1(it + 1, j + 2 - NCH);
+          }
         }
       }
       if (PROF) lacc[7] = clock64() - t_role;
@@ -377,7 +457,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       constexpr int CW = C / 2;                              // columns of this warp
       const int cbase = half * CW;
       uint4 rbuf[8];
-      ml_res_issue(p.res, (p.dbg & 4) ? -1 : orow, C, cbase, lane, rbuf);
+      ml_res_issue(p.res, (PJ || (p.dbg & 4)) ? -1 : orow, C, cbase, lane, rbuf);   // PJ: residual already inside acc2
       { ML_T0(); ptx::mbar_wait(c2_full, t & 1); ML_ACC(10); }
       ptx::tc_fence_after();
       ML_T0();
@@ -429,7 +509,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
             }
             // this register is free again: fetch the same piece of the next 32-column slice
             if (c0 + 32 < CW)
-              rbuf[u * 4 + i] = (orr >= 0 && !(p.dbg & 4))
+              rbuf[u * 4 + i] = (!PJ && orr >= 0 && !(p.dbg & 4))
                                     ? *reinterpret_cast<const uint4*>(p.res + (size_t)orr * C + cbase + c0 + 32 + u * 16 + seg * 4)
                                     : make_uint4(0u, 0u, 0u, 0u);
           }
@@ -439,8 +519,105 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       ML_ACC(11);
     };
 
+    // epilogue 0 (PJ): s = o.Wp^T + bp + residual; acc2 <- s + b2 (the seed of GEMM 2); A buffer <- LayerNorm(s)
+    auto epi0 = [&](int t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int m = tile * ML_BM + r;
+      int32_t orow = -1;
+      if (m < p.M) orow = p.out_rows ? __ldg(p.out_rows + m) : m;
+      constexpr int CW = C / 2;
+      const int cbase = half * CW;
+      const float* v_bp = s_pj + cbase;
+      const float* v_g = s_pj + C + cbase;
+      const float* v_be = s_pj + 2 * C + cbase;
+      const float* v_b2 = s_pj + 3 * C + cbase;
+      uint4 rbuf[8];
+      ml_res_issue(p.res, orow, C, cbase, lane, rbuf);
+      ptx::mbar_wait(c0_full, t & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_src = lane_base + cbase, t_dst = lane_base + 256 + cbase;
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CW; c0 += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld32(t_src + c0, raw);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(v_bp + c0 + 4 * q);
+          v[4 * q] = __uint_as_float(raw[4 * q]) + b.x;
+          v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+          v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+          v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+        }
+        ml_res_add(stage, lane, rbuf, v);
+        if (c0 + 32 < CW) ml_res_issue(p.res, orow, C, cbase + c0 + 32, lane, rbuf);
+        if (c0 == 0) shift = v[0];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(v_b2 + c0 + 4 * q);
+          const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d = v[4 * q + e] - shift;
+            s1 += d; s2 = fmaf(d, d, s2);
+            raw[4 * q + e] = __float_as_uint(v[4 * q + e] + bb[e]);
+          }
+        }
+        ptx::tmem_st32(t_dst + c0, raw);
+      }
+      // per-half (mean, M2) -> exchange with the warp that owns the other column half of this row
+      const float nh = (float)CW;
+      const float mean_h = shift + s1 / nh;
+      const float m2_h = s2 - s1 * s1 / nh;
+      s_lnx[half * 128 + r] = make_float2(mean_h, m2_h);
+      ptx::tmem_st_wait();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      const float2 o = s_lnx[(half ^ 1) * 128 + r];
+      const float delta = o.x - mean_h;
+      const float mean = mean_h + 0.5f * delta;
+      const float var = (m2_h + o.y + delta * delta * nh * 0.5f) / (2.f * nh);
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + p.ln_eps);
+#pragma unroll 1
+      for (int c0 = 0; c0 < CW; c0 += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld32(t_dst + c0, raw);
+        ptx::tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 gm = *reinterpret_cast<const float4*>(v_g + c0 + 4 * q);
+          const float4 bt = *reinterpret_cast<const float4*>(v_be + c0 + 4 * q);
+          const float4 b2 = *reinterpret_cast<const float4*>(v_b2 + c0 + 4 * q);
+          const float y0 = (__uint_as_float(raw[4 * q]) - b2.x - mean) * rstd * gm.x + bt.x;
+          const float y1 = (__uint_as_float(raw[4 * q + 1]) - b2.y - mean) * rstd * gm.y + bt.y;
+          const float y2 = (__uint_as_float(raw[4 * q + 2]) - b2.z - mean) * rstd * gm.z + bt.z;
+          const float y3 = (__uint_as_float(raw[4 * q + 3]) - b2.w - mean) * rstd * gm.w + bt.w;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+          w[2 * q] = *reinterpret_cast<uint32_t*>(&h0);
+          w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        // row r of the K-major 128B-swizzled operand: K block = 64 columns, 16-byte chunk c at (c ^ (r & 7))
+        const int col = cbase + c0, kb = col >> 6, ch0 = (col & 63) >> 3;
+        const uint32_t rowa = sA1 + kb * ML_STAGE + (uint32_t)r * 128u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          ml_sts128(rowa + (uint32_t)(((ch0 + q) ^ (r & 7)) << 4), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        if (((col + 32) & 63) == 0) {                        // this warp's share of K block kb is complete
+          ptx::fence_proxy_async();                          // generic-proxy stores -> UMMA (async proxy)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(a1_full + 8 * kb);
+        }
+      }
+      // the exchange slot is rewritten only after both halves passed this barrier
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+    };
+
     // static schedule: the final tile of iteration t - 1 is written out between the first two
     // chunks of iteration t, when its GEMM 2 has long finished and acc2 is about to be reused
+    // (PJ: before epilogue 0 of iteration t, which re-seeds acc2)
     for (int it = 0; it < n_my; ++it) {
       {                                                      // pull this tile's residual rows (of this warp's column half) into L2; they are read one tile later
         const int m = (blockIdx.x + it * gridDim.x) * ML_BM + r;
@@ -451,9 +628,15 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
           for (int k = 0; k < C * 2 / 128; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + k * 128));
         }
       }
-      epi1(it, 0);
-      if (it > 0) epi2(it - 1);
-      for (int j = 1; j < NCH; ++j) epi1(it, j);
+      if constexpr (PJ) {
+        if (it > 0) epi2(it - 1);
+        epi0(it);
+        for (int j = 0; j < NCH; ++j) epi1(it, j);
+      } else {
+        epi1(it, 0);
+        if (it > 0) epi2(it - 1);
+        for (int j = 1; j < NCH; ++j) epi1(it, j);
+      }
     }
     if (n_my > 0) epi2(n_my - 1);
     if (PROF) lacc[12] = clock64() - t_role;
@@ -489,37 +672,27 @@ static PFN_encodeTiled2 mlp_get_encode() {
   return fn;
 }
 
-template <int C, bool PROF>
-static int launch_mlp(const CUtensorMap& t1, const CUtensorMap& t2, const MlpParams& p, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    HFL_CUDA(cudaFuncSetAttribute(k_mlp_fused<C, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  MlpSmem<C>::TOTAL));
-    attr = true;
-  }
+template <int C, bool PROF, bool PJ>
+static int launch_mlp(const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& to, const CUtensorMap& tp,
+                      const MlpParams& p, cudaStream_t st) {
+  // the attribute is per device: set it on every launch (cheap) instead of caching a process-wide flag
+  HFL_CUDA(cudaFuncSetAttribute(k_mlp_fused<C, PROF, PJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MlpSmem<C, PJ>::TOTAL));
   const int m_tiles = (p.M + ML_BM - 1) / ML_BM;
-  const int grid = m_tiles < kSMs ? m_tiles : kSMs;
-  HFL_LAUNCH((k_mlp_fused<C, PROF><<<grid, ML_THREADS, MlpSmem<C>::TOTAL, st>>>(t1, t2, p)));
+  const int sms = sm_count();
+  const int grid = m_tiles < sms ? m_tiles : sms;
+  HFL_LAUNCH((k_mlp_fused<C, PROF, PJ><<<grid, ML_THREADS, MlpSmem<C, PJ>::TOTAL, st>>>(t1, t2, to, tp, p)));
   return HFL_OK;
 }
 
-}  // namespace hfl
-
-using namespace hfl;
-
-extern "C" {
-
-int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, const float* b2,
-                  int64_t M, int32_t C, const float* res, float* out_f32, void* out_bf16,
-                  const int32_t* out_rows, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (M == 0) return HFL_OK;
-  HFL_CHECK_ARG(A && W1 && b1 && W2 && b2 && res && out_f32, "null argument");
-  HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
-  HFL_CHECK_ARG(M > 0 && M < (1ll << 31), "bad M");
+static int mlp_dispatch(const void* A, const void* Wp, const float* bp, const float* ln_g, const float* ln_b,
+                        const void* W1, const float* b1, const void* W2, const float* b2, int64_t M, int32_t C,
+                        const float* res, float* out_f32, void* out_bf16, const int32_t* out_rows,
+                        cudaStream_t st) {
+  const bool pj = Wp != nullptr;
   PFN_encodeTiled2 enc = mlp_get_encode();
   if (!enc) return fail(HFL_ERR_CUDA, "cuTensorMapEncodeTiled unavailable%s", "");
-  CUtensorMap t1, t2;
+  CUtensorMap t1, t2, to, tp;
   // 3-D views {64 K-columns, rows, K blocks of 64}: one box = consecutive 16 KB K-major UMMA tiles
   auto make_map = [&](CUtensorMap* tm, const void* W, int rows, int cols, int box_rows, int box_kb) -> CUresult {
     cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
@@ -533,15 +706,31 @@ int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2
   if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W1) failed%s (%lld)", "", (long long)cr);
   cr = C == 256 ? make_map(&t2, W2, C, 4 * C, 256, 1) : make_map(&t2, W2, C, 4 * C, 128, 2);
   if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W2) failed%s (%lld)", "", (long long)cr);
+  to = t1; tp = t1;
+  if (pj) {
+    cr = C == 256 ? make_map(&tp, Wp, C, C, 256, 1) : make_map(&tp, Wp, C, C, 128, 2);
+    if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (Wp) failed%s (%lld)", "", (long long)cr);
+    // o tile: 128 x 64 boxes of the row-major [M, C] matrix, rows >= M zero-filled
+    cuuint64_t adims[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    cuuint64_t astr[1] = {(cuuint64_t)C * 2};
+    cuuint32_t abox[2] = {64, (cuuint32_t)ML_BM}, es[2] = {1, 1};
+    cr = enc(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A), adims, astr, abox, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (o) failed%s (%lld)", "", (long long)cr);
+  }
   static long long* prof = nullptr;
-  const bool want_prof = getenv("HFL_MLP_PROF") != nullptr;
+  static const bool want_prof = getenv("HFL_MLP_PROF") != nullptr;
+  static const int dbg = getenv("HFL_MLP_DBG") ? atoi(getenv("HFL_MLP_DBG")) : 0;
   if (want_prof && !prof) cudaMalloc(&prof, 32 * sizeof(long long));
   if (want_prof) cudaMemsetAsync(prof, 0, 32 * sizeof(long long), st);
   MlpParams p{(const __nv_bfloat16*)A, (int)M, b1, b2, res, out_f32, (__nv_bfloat16*)out_bf16, out_rows,
-              getenv("HFL_MLP_DBG") ? atoi(getenv("HFL_MLP_DBG")) : 0, want_prof ? prof : nullptr};
-  const int rc = want_prof ? (C == 128 ? launch_mlp<128, true>(t1, t2, p, st) : launch_mlp<256, true>(t1, t2, p, st))
-                           : (C == 128 ? launch_mlp<128, false>(t1, t2, p, st) : launch_mlp<256, false>(t1, t2, p, st));
-  if (want_prof && rc == HFL_OK) {
+              dbg, (want_prof && !pj) ? prof : nullptr, bp, ln_g, ln_b, 1e-5f};
+  int rc;
+  if (pj) rc = C == 128 ? launch_mlp<128, false, true>(t1, t2, to, tp, p, st) : launch_mlp<256, false, true>(t1, t2, to, tp, p, st);
+  else if (want_prof) rc = C == 128 ? launch_mlp<128, true, false>(t1, t2, to, tp, p, st) : launch_mlp<256, true, false>(t1, t2, to, tp, p, st);
+  else rc = C == 128 ? launch_mlp<128, false, false>(t1, t2, to, tp, p, st) : launch_mlp<256, false, false>(t1, t2, to, tp, p, st);
+  if (want_prof && !pj && rc == HFL_OK) {
     long long h[32];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
@@ -554,6 +743,35 @@ int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2
     fprintf(stderr, "\n");
   }
   return rc;
+}
+
+}  // namespace hfl
+
+using namespace hfl;
+
+extern "C" {
+
+int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2, const float* b2,
+                  int64_t M, int32_t C, const float* res, float* out_f32, void* out_bf16,
+                  const int32_t* out_rows, void* stream_) {
+  if (M == 0) return HFL_OK;
+  HFL_CHECK_ARG(A && W1 && b1 && W2 && b2 && res && out_f32, "null argument");
+  HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
+  HFL_CHECK_ARG(M > 0 && M < (1ll << 31), "bad M");
+  return mlp_dispatch(A, nullptr, nullptr, nullptr, nullptr, W1, b1, W2, b2, M, C, res, out_f32, out_bf16,
+                      out_rows, (cudaStream_t)stream_);
+}
+
+int hfl_proj_mlp_fused(const void* O, const void* Wp, const float* bp, const float* ln_g, const float* ln_b,
+                       const void* W1, const float* b1, const void* W2, const float* b2, int64_t M, int32_t C,
+                       const float* res, float* out_f32, void* out_bf16, const int32_t* out_rows,
+                       void* stream_) {
+  if (M == 0) return HFL_OK;
+  HFL_CHECK_ARG(O && Wp && bp && ln_g && ln_b && W1 && b1 && W2 && b2 && res && out_f32, "null argument");
+  HFL_CHECK_ARG(C == 128 || C == 256, "C must be 128 or 256");
+  HFL_CHECK_ARG(M > 0 && M < (1ll << 31), "bad M");
+  return mlp_dispatch(O, Wp, bp, ln_g, ln_b, W1, b1, W2, b2, M, C, res, out_f32, out_bf16, out_rows,
+                      (cudaStream_t)stream_);
 }
 
 }  // extern "C"

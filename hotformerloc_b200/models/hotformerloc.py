@@ -280,6 +280,13 @@ def _fused_mlp(C: int) -> bool:
     return str(C) in os.environ.get('HFL_FUSED_MLP', '128,256').split(',')
 
 
+def _fused_proj_mlp() -> bool:
+    """HFL_FUSED_PROJ=0 selects the round-1 schedule (proj GEMM with residual + LayerNorm epilogue,
+    then the MLP kernel); default: one kernel for proj + residual + norm2 + MLP + residual."""
+    import os
+    return os.environ.get('HFL_FUSED_PROJ', '1') != '0'
+
+
 def _bf(t):
     return t.detach().to(torch.bfloat16).contiguous()
 
@@ -394,6 +401,10 @@ class _Engine:
                    K if hat else 0)
         ops.gather_gemm(y, bw['qkv'][0], bias=bw['qkv'][1], out_v_bf16=qkv)
         ops.window_attn(qkv, o, tok, bw['rpe'], n_win, H, C, K, bw['dil'], hat, bw['bnd'], 0.25)
+        if _fused_proj_mlp():
+            ops.proj_mlp_fused(o, bw['proj'][0], bw['proj'][1], bw['n2'][0], bw['n2'][1], bw['fc1'][0],
+                               bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=x, out_f32=x, out_bf16=xb)
+            return
         ops.gather_gemm(o, bw['proj'][0], bias=bw['proj'][1], res=x, out_v_f32=x, ln=bw['n2'],
                         out_y_bf16=y)
         if _fused_mlp(C):
@@ -534,10 +545,15 @@ class _Engine:
             ops.ln_rows(X, tabs['rt_rows'], T, C1, bw['n1'][0], bw['n1'][1], yr)
             ops.gather_gemm(yr, bw['qkv'][0], bias=bw['qkv'][1], out_v_bf16=qkvr)
             ops.varlen_attn(qkvr, orr, tabs['cu'], tabs['ids'], B, tabs['max_len'], H1, C1, 0.25)
-            ops.gather_gemm(orr, bw['proj'][0], bias=bw['proj'][1], res=X, out_v_f32=X,
-                            ln=bw['n2'], out_y_bf16=yr, out_rows=tabs['rt_rows'])
-            ops.mlp_fused(yr, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X, out_f32=X,
-                          out_rows=tabs['rt_rows'])
+            if _fused_proj_mlp():
+                ops.proj_mlp_fused(orr, bw['proj'][0], bw['proj'][1], bw['n2'][0], bw['n2'][1],
+                                   bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X,
+                                   out_f32=X, out_rows=tabs['rt_rows'])
+            else:
+                ops.gather_gemm(orr, bw['proj'][0], bias=bw['proj'][1], res=X, out_v_f32=X,
+                                ln=bw['n2'], out_y_bf16=yr, out_rows=tabs['rt_rows'])
+                ops.mlp_fused(yr, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X,
+                              out_f32=X, out_rows=tabs['rt_rows'])
             if lvl_streams is None:
                 for j in range(L):
                     self._block(w['hosa'][j][i], Xl[j], Xbl[j], ne[j], tok[j], nl[j], rows[j], nwin[j],

@@ -43,6 +43,16 @@ def mlp_fused(A, W1, b1, W2, b2, *, res, out_f32, out_bf16=None, out_rows=None, 
                                   C, _p(res), _p(out_f32), _p(out_bf16), _p(out_rows), _s()))
 
 
+def proj_mlp_fused(O, Wp, bp, ln_g, ln_b, W1, b1, W2, b2, *, res, out_f32, out_bf16=None, out_rows=None,
+                   M=None):
+    """s = res[orow] + O Wp^T + bp ; x[orow] = s + fc2(GELU(fc1(LN(s)))) (hfl_proj_mlp_fused)."""
+    C = O.shape[1]
+    assert Wp.shape == (C, C) and W1.shape == (4 * C, C) and W2.shape == (C, 4 * C)
+    N.check(N.lib().hfl_proj_mlp_fused(_p(O), _p(Wp), _p(bp), _p(ln_g), _p(ln_b), _p(W1), _p(b1), _p(W2),
+                                       _p(b2), O.shape[0] if M is None else M, C, _p(res), _p(out_f32),
+                                       _p(out_bf16), _p(out_rows), _s()))
+
+
 def window_attn(qkv, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
     N.check(N.lib().hfl_window_attn(_p(qkv), _p(out), _p(xyzb), _p(rpe), n_win, H, C, K, dil,
                                     int(hat), bnd, float(scale), _s()))

@@ -124,6 +124,17 @@ int hfl_mlp_fused(const void* A, const void* W1, const float* b1, const void* W2
                   int64_t M, int32_t C, const float* res, float* out_f32, void* out_bf16,
                   const int32_t* out_rows, void* stream);
 
+/* Attention output projection + residual + norm2 + MLP + residual in one kernel:
+ *   s = res[orow] + O . Wp^T + bp ;  out[orow] = s + fc2(GELU(fc1(LayerNorm(s)) + b1)) + b2
+ * O: [M, C] bf16 attention output (before proj), Wp: [C, C] bf16.  The projected tile, norm2 and the
+ * hidden activation never leave the SM; the fp32 residual stream is read and written once.
+ * Replaces `x = x + proj(attn)` + `x = x + mlp(norm2(x))` of the pre-LN blocks
+ * (octformer_backbone.py:276-281, hotformerloc_backbone.py:212-216, 287-291). */
+int hfl_proj_mlp_fused(const void* O, const void* Wp, const float* bp, const float* ln_g,
+                       const float* ln_b, const void* W1, const float* b1, const void* W2,
+                       const float* b2, int64_t M, int32_t C, const float* res, float* out_f32,
+                       void* out_bf16, const int32_t* out_rows, void* stream);
+
 /* Octree window attention core (octformer_backbone.py:52-93 + RPE octformer_layers.py:144-170):
  * softmax(q k^T * scale + [same-submap mask] + RPE) v per (window, head), head_dim 16.
  * Window w holds K tokens: plain rows w*K+s; dilated rows (w/dil)*K*dil + s*dil + w%dil;

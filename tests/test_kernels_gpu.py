@@ -116,6 +116,34 @@ def test_mlp_fused(C, M, mapped):
     assert torch.allclose(xb.float()[sel], ref[sel], atol=5e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize('C,M,mapped', [(256, 5000, False), (128, 3001, False), (256, 777, True),
+                                        (256, 300000, False), (256, 100, False), (128, 1, False),
+                                        (128, 128 * 148 + 5, True), (256, 128 * 148 * 2, False)])
+def test_proj_mlp_fused(C, M, mapped):
+    """x = x + proj(o); x = x + mlp(norm2(x)) in one kernel vs fp32 torch."""
+    torch.manual_seed(9)
+    o = _bf(torch.randn(M, C, device=DEV))
+    Wp = _bf(torch.randn(C, C, device=DEV) / math.sqrt(C))
+    W1 = _bf(torch.randn(4 * C, C, device=DEV) / math.sqrt(C))
+    W2 = _bf(torch.randn(C, 4 * C, device=DEV) / math.sqrt(4 * C))
+    bp, b1, b2 = (torch.randn(n, device=DEV) * 0.1 for n in (C, 4 * C, C))
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    R = M + 500 if mapped else M
+    rows = torch.randperm(R, device=DEV)[:M].to(torch.int32) if mapped else None
+    x = torch.randn(R, C, device=DEV) * 2 + 0.5
+    x0 = x.clone()
+    xb = torch.zeros(R, C, device=DEV, dtype=torch.bfloat16)
+    _ops().proj_mlp_fused(o, Wp, bp, g, b, W1, b1, W2, b2, res=x, out_f32=x, out_bf16=xb, out_rows=rows)
+    sel = rows.long() if mapped else slice(None)
+    s = x0[sel] + o.float() @ Wp.float().t() + bp
+    y = _bf(F.layer_norm(s, (C,), g, b, 1e-5)).float()                  # operand rounded to bf16 as on chip
+    h = _bf(F.gelu(y @ W1.float().t() + b1)).float()
+    ref = x0.clone()
+    ref[sel] = s + h @ W2.float().t() + b2
+    assert torch.allclose(x, ref, atol=1e-2, rtol=2e-3), (x - ref).abs().max()
+    assert torch.allclose(xb.float()[sel], ref[sel], atol=5e-2, rtol=1e-2)
+
+
 def _tokens(n_pad, n, B, K):
     xyz = torch.randint(0, 128, (n_pad, 3), dtype=torch.int16)
     bid = torch.sort(torch.randint(0, B, (n_pad,))).values.to(torch.int16)
