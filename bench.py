@@ -149,7 +149,13 @@ def kernel_profile(model, octree_fn):
         return {'flop': 2.0 * M * C * C + 4.0 * M * W1.shape[0] * W1.shape[1],
                 'byte': float(M * C * (2 + 4 + 4 + (2 if k.get('out_bf16') is not None else 0)))}
 
-    patches = {'gather_gemm': gemm_work, 'window_attn': attn_work, 'cpe_ln': cpe_work,
+    def qkv_attn_work(y, Wg, bg, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
+        L = K + (1 if hat else 0)
+        rows = n_win * L
+        return {'flop': 2.0 * rows * C * 3 * C + 4.0 * n_win * L * L * C,
+                'byte': float(rows * (C * 2 + C * 2) + n_win * K * 8 + 3 * C * C * 2)}
+
+    patches = {'qkv_attn': qkv_attn_work, 'gather_gemm': gemm_work, 'window_attn': attn_work, 'cpe_ln': cpe_work,
                'mlp_fused': mlp_work, 'proj_mlp_fused': proj_mlp_work}
     for name, work in patches.items():
         saved[name] = getattr(ops, name)

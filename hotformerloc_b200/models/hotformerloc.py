@@ -280,6 +280,13 @@ def _fused_mlp(C: int) -> bool:
     return str(C) in os.environ.get('HFL_FUSED_MLP', '128,256').split(',')
 
 
+def _fused_attn() -> bool:
+    """HFL_FUSED_ATTN=0 selects the qkv GEMM + stand-alone window attention kernels; default: the fused
+    tensor-core kernel (hfl_qkv_attn) wherever it supports the window shape."""
+    import os
+    return os.environ.get('HFL_FUSED_ATTN', '1') != '0'
+
+
 def _fused_proj_mlp() -> bool:
     """HFL_FUSED_PROJ=0 selects the round-1 schedule (proj GEMM with residual + LayerNorm epilogue,
     then the MLP kernel); default: one kernel for proj + residual + norm2 + MLP + residual."""
@@ -332,6 +339,8 @@ class _Engine:
                      fc2=(_bf(b.mlp.fc2.weight), _f(b.mlp.fc2.bias)))
             att = b.attention if hasattr(b, 'attention') else b.rt_attention
             d['qkv'] = (_bf(att.qkv.weight), _f(att.qkv.bias))
+            if hasattr(b, 'cpe') and att.qkv.weight.shape[1] % 64 == 0:
+                d['qkv_g'] = ops.regroup_qkv(*d['qkv'])          # per-4-head [q | k | v] rows (hfl_qkv_attn)
             d['proj'] = (_bf(att.proj.weight), _f(att.proj.bias))
             if hasattr(att, 'rpe'):
                 d['rpe'] = _f(att.rpe.rpe_table)
@@ -399,8 +408,12 @@ class _Engine:
         cw, cg, cb = bw['cpe']
         ops.cpe_ln(x, xb, ne, cw, cg, cb, bw['n1'][0], bw['n1'][1], y, None, n, rows, C,
                    K if hat else 0)
-        ops.gather_gemm(y, bw['qkv'][0], bias=bw['qkv'][1], out_v_bf16=qkv)
-        ops.window_attn(qkv, o, tok, bw['rpe'], n_win, H, C, K, bw['dil'], hat, bw['bnd'], 0.25)
+        if _fused_attn() and 'qkv_g' in bw and ops.qkv_attn_supported(H, C, K, bw['dil'], hat, bw['bnd']):
+            ops.qkv_attn(y, bw['qkv_g'][0], bw['qkv_g'][1], o, tok, bw['rpe'], n_win, H, C, K, bw['dil'],
+                         hat, bw['bnd'], 0.25)
+        else:
+            ops.gather_gemm(y, bw['qkv'][0], bias=bw['qkv'][1], out_v_bf16=qkv)
+            ops.window_attn(qkv, o, tok, bw['rpe'], n_win, H, C, K, bw['dil'], hat, bw['bnd'], 0.25)
         if _fused_proj_mlp():
             ops.proj_mlp_fused(o, bw['proj'][0], bw['proj'][1], bw['n2'][0], bw['n2'][1], bw['fc1'][0],
                                bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=x, out_f32=x, out_bf16=xb)

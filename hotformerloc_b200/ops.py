@@ -58,6 +58,24 @@ def window_attn(qkv, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
                                     int(hat), bnd, float(scale), _s()))
 
 
+def regroup_qkv(W: torch.Tensor, b: torch.Tensor):
+    """nn.Linear(C, 3C) weight / bias -> the per-4-head [q | k | v] row order hfl_qkv_attn reads."""
+    C = W.shape[1]
+    idx = torch.cat([torch.arange(64) + part * C + g * 64 for g in range(C // 64) for part in range(3)])
+    idx = idx.to(W.device)
+    return W[idx].contiguous(), b[idx].contiguous()
+
+
+def qkv_attn_supported(H, C, K, dil, hat, bnd) -> bool:
+    return bool(N.lib().hfl_qkv_attn_supported(H, C, K, dil, int(hat), bnd))
+
+
+def qkv_attn(y, Wg, bias_g, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
+    """out = window attention of (y Wqkv^T + b), qkv never materialised (hfl_qkv_attn)."""
+    N.check(N.lib().hfl_qkv_attn(_p(y), _p(Wg), _p(bias_g), _p(out), _p(xyzb), _p(rpe), n_win, y.shape[0],
+                                 H, C, K, dil, int(hat), bnd, float(scale), _s()))
+
+
 def varlen_attn(qkv, out, cu, ids, B, max_len, H, C, scale):
     N.check(N.lib().hfl_varlen_attn(_p(qkv), _p(out), _p(cu), _p(ids), B, max_len, H, C,
                                     float(scale), _s()))

@@ -143,6 +143,19 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
                     int64_t n_win, int32_t H, int32_t C, int32_t K, int32_t dil, int32_t hat,
                     int32_t bnd, float scale, void* stream);
 
+/* Fused qkv projection + octree window attention (everything of OctreeAttention.forward before `proj`,
+ * octformer_backbone.py:52-88): out = softmax(q k^T * scale + mask + RPE) v with q, k, v = y Wqkv^T + b
+ * computed on chip (tcgen05: projection, q k^T and p v; the [rows, 3C] qkv tensor never exists).
+ * y: [rows, C] bf16 LayerNorm'ed tokens in the window layout of hfl_window_attn.  Wg / bias_g: the
+ * nn.Linear(C, 3C) weight [3C, C] bf16 / bias with rows regrouped per 4 heads as [q(64) | k(64) | v(64)]
+ * (hotformerloc_b200.ops.regroup_qkv).  hfl_qkv_attn_supported() tells whether a configuration is
+ * handled (window length K + hat in {16,17,32,33,48,49,64}, C in {128,256}); otherwise use
+ * hfl_gather_gemm + hfl_window_attn. */
+int hfl_qkv_attn_supported(int32_t H, int32_t C, int32_t K, int32_t dil, int32_t hat, int32_t bnd);
+int hfl_qkv_attn(const void* y, const void* Wg, const float* bias_g, void* out, const int16_t* xyzb,
+                 const float* rpe, int64_t n_win, int64_t rows, int32_t H, int32_t C, int32_t K,
+                 int32_t dil, int32_t hat, int32_t bnd, float scale, void* stream);
+
 /* Relay-token self-attention over ragged per-submap sequences
  * (hotformerloc_backbone.py:83-119 with the mask of models/octree.py:229-265). */
 int hfl_varlen_attn(const void* qkv, void* out, const int32_t* cu_seqlens, const int32_t* ids,

@@ -206,6 +206,41 @@ def test_window_attention(K, dil, hat, H):
     assert err < 3e-2, err            # bf16 probabilities / outputs
 
 
+@pytest.mark.parametrize('K,dil,hat,H', [(48, 1, False, 8), (48, 4, False, 8), (48, 1, True, 16),
+                                         (64, 4, False, 8), (32, 1, True, 8), (32, 1, False, 16),
+                                         (64, 1, False, 16), (16, 1, True, 8)])
+@pytest.mark.parametrize('n_groups', [5, 301])
+def test_qkv_attn_fused(K, dil, hat, H, n_groups):
+    """fused projection + tensor-core window attention vs fp32 torch on the bf16-rounded qkv."""
+    torch.manual_seed(13)
+    C = 16 * H
+    if not _ops().qkv_attn_supported(H, C, K, dil, hat, int(0.8 * K * dil ** 0.5)):
+        pytest.skip('configuration handled by the unfused path')
+    n_pad, B = K * 4 * n_groups, 7
+    n = n_pad - 37
+    tok = _tokens(n_pad, n, B, K)
+    n_win = n_pad // K
+    rows = n_win * (K + 1) if hat else n_pad
+    y = _bf(torch.randn(rows, C, device=DEV))
+    W = _bf(torch.randn(3 * C, C, device=DEV) / math.sqrt(C))
+    b = torch.randn(3 * C, device=DEV) * 0.2
+    bnd = int(0.8 * K * dil ** 0.5)
+    rpe = (torch.randn(3 * (2 * bnd + 1), H) * 0.5).to(DEV)
+    Wg, bg = _ops().regroup_qkv(W, b)
+    out = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
+    _ops().qkv_attn(y, Wg, bg, out, tok.to(DEV), rpe, n_win, H, C, K, dil, hat, bnd, 0.25)
+    qkv = _bf(y.float() @ W.float().t() + b)
+    ref = _ref_window_attn(qkv, tok, rpe, K, dil, hat, H, bnd)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err < 3e-2, err
+    # no RPE (disable_RPE)
+    out.zero_()
+    _ops().qkv_attn(y, Wg, bg, out, tok.to(DEV), None, n_win, H, C, K, dil, hat, bnd, 0.25)
+    ref = _ref_window_attn(qkv, tok, None, K, dil, hat, H, bnd)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err < 3e-2, err
+
+
 def test_varlen_attention():
     torch.manual_seed(4)
     H, C = 16, 256
