@@ -40,7 +40,7 @@ UNIT = 'submaps/s'
 
 
 def synthetic_batches(n_batches, B, P, seed0=1000):
-    from oracle.model_ref import lidar_cloud          # generator only (shared with the tests)
+    from hotformerloc_b200.datasets.synthetic import lidar_cloud
     out = []
     for i in range(n_batches):
         g = torch.Generator().manual_seed(seed0 + i)

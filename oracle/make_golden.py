@@ -193,6 +193,53 @@ def make_recall_golden():
     print('recall golden written')
 
 
+def make_normalize_golden():
+    """Reference ``Normalize`` (datasets/augmentation.py:185-235) on a metric-scale cloud, every mode the
+    eval path can select (config keys normalize_points / scale_factor / unit_sphere_norm) -> normalize.npz."""
+    S.install()
+    from datasets.augmentation import Normalize
+    from hotformerloc_b200.datasets.synthetic import trajectory_clouds
+    cloud = trajectory_clouds(1, 1, 6000, seed=3)[0][0].astype(np.float32)
+    out = {'cloud': cloud}
+    variants = {'bbox': {}, 'scale30': dict(scale_factor=30.0), 'sphere': dict(unit_sphere_norm=True),
+                'sphere_scale40': dict(unit_sphere_norm=True, scale_factor=40.0),
+                'range2': dict(norm_range=2.0), 'bbox_nocenter': dict(zero_mean=False)}
+    for name, kw in variants.items():
+        out[name] = Normalize(**kw)(torch.from_numpy(cloud).clone()).numpy()
+    np.savez_compressed(os.path.join(OUT, 'normalize.npz'), **out)
+    print('normalize golden written')
+
+
+def make_gem_golden():
+    """pooling=PyramidOctGeM through the reference's own model code (models/layers/pooling.py:58-103):
+    state_dict layout + descriptors of a 3-submap Oxford batch -> state_shapes_oxford_gem.json,
+    descriptors_gem.npz."""
+    import tempfile
+    S.install()
+    cfg = open(f'{REF}/models/hotformerloc_oxford_cfg.txt').read()
+    lines = [('pooling = PyramidOctGeM' if l.split('=')[0].strip() == 'pooling' else l) for l in cfg.splitlines()]
+    path = os.path.join(tempfile.mkdtemp(prefix='hfl_gem_'), 'hotformerloc_oxford_gem_cfg.txt')
+    open(path, 'w').write('\n'.join(lines) + '\n')
+    m = S.reference_model(path)
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, 'state_shapes_oxford_gem.json'), 'w') as f:
+        json.dump(shapes, f, indent=0)
+    m.load_state_dict(M.synthetic_state_dict({k: tuple(v) for k, v in shapes.items()}, mode='stress'))
+    g = torch.Generator().manual_seed(9)
+    clouds = [M.lidar_cloud(4096, g) for _ in range(3)]
+    with torch.inference_mode():
+        y = m(S.make_batch(clouds, 9))['global'].numpy()
+    np.savez_compressed(os.path.join(OUT, 'descriptors_gem.npz'), reference=y)
+    print('GeM golden written')
+
+
 if __name__ == '__main__':
-    main()
-    make_recall_golden()
+    which = sys.argv[1:] or ['main', 'recall', 'normalize', 'gem']
+    if 'main' in which:
+        main()
+    if 'recall' in which:
+        make_recall_golden()
+    if 'normalize' in which:
+        make_normalize_golden()
+    if 'gem' in which:
+        make_gem_golden()

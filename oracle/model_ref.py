@@ -418,17 +418,9 @@ def forward(sd: Dict[str, torch.Tensor], oct: R.RefOctree, hp: HParams,
 # ----------------------------------------------------------------------------
 # deterministic synthetic inputs / weights shared by oracle, tests and bench
 # ----------------------------------------------------------------------------
-def lidar_cloud(n: int, g: torch.Generator, aerial: bool = False) -> np.ndarray:
-    """Synthetic 'lidar-ish' cloud of SURVEY.md Appendix C.5 / section 8d."""
-    xy = (torch.rand(n, 2, generator=g) * 2 - 1) * 0.95
-    m = torch.rand(n, generator=g) < (0.3 if aerial else 0.6)
-    if aerial:
-        z = torch.where(m, 0.02 * torch.randn(n, generator=g) - 0.3,
-                        torch.rand(n, generator=g) * 0.9 - 0.2)
-    else:
-        z = torch.where(m, 0.02 * torch.randn(n, generator=g) - 0.3,
-                        torch.rand(n, generator=g) * 0.8 - 0.3)
-    return torch.cat([xy, z[:, None]], 1).clamp(-1, 1).numpy()
+# the synthetic cloud generator lives with the other workload generators (shared by bench.py, the
+# tools and the tests); re-exported here for the parity tests
+from hotformerloc_b200.datasets.synthetic import lidar_cloud  # noqa: E402,F401
 
 
 def synthetic_state_dict(shapes: Dict[str, Sequence[int]], seed: int = 0,

@@ -82,6 +82,19 @@ def test_loaders(tmp_path):
                           np.delete(pts.astype(np.float32), 7, axis=0))
 
 
+def test_normalize_matches_reference_golden():
+    """Normalize (datasets/augmentation.py:185-235) in every mode the eval configs can select:
+    bit-exact against outputs of the reference's own class (oracle/make_golden.py:make_normalize_golden)."""
+    from hotformerloc_b200.datasets.coordinate_utils import Normalize
+    g = np.load(os.path.join(GOLDEN, 'normalize.npz'))
+    variants = {'bbox': {}, 'scale30': dict(scale_factor=30.0), 'sphere': dict(unit_sphere_norm=True),
+                'sphere_scale40': dict(unit_sphere_norm=True, scale_factor=40.0),
+                'range2': dict(norm_range=2.0), 'bbox_nocenter': dict(zero_mean=False)}
+    for name, kw in variants.items():
+        out = Normalize(**kw)(torch.from_numpy(g['cloud']).clone()).numpy()
+        assert np.array_equal(out, g[name]), name
+
+
 def test_cylindrical_matches_reference_golden():
     from hotformerloc_b200.datasets.coordinate_utils import cylindrical_for_octree
     g = np.load(os.path.join(GOLDEN, 'cylindrical.npz'))

@@ -2,6 +2,7 @@
 statement of the same op (on the same bf16-rounded operands).  Tolerances are
 written next to each check."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -344,3 +345,151 @@ def test_knn_matches_bruteforce():
     parts = [(_ops().knn_topk(q, db[s:s + 1000], 25, idx_offset=s)) for s in (0, 1000, 2000)]
     md, mi = _ops().topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
     assert torch.equal(mi, i) and torch.equal(md, d)
+
+
+# ---------------------------------------------------------------------------
+# relay-token / pooling-head kernels in isolation
+# ---------------------------------------------------------------------------
+def _hat(n_tok, K):
+    """hat-layout rows of tokens 0..n_tok-1 (relay token first in every window)."""
+    t = torch.arange(n_tok)
+    return t + t // K + 1
+
+
+@pytest.mark.parametrize('name,K', [('cswp_b6_stress', 64), ('oxford_b4_init', 48)])
+def test_rt_init_vs_reference_octree_t(name, K):
+    """hfl_rt_init: masked window mean + ADaPE window statistics + fc1/GELU against the values the
+    reference's own OctreeT produced (tests/golden/octree_t.npz: rt_init_mask, window_stats) --
+    includes windows shared by several submaps and pure-padding windows."""
+    from oracle.make_golden import CASES
+    from tests.common import GOLDEN, case_clouds
+    from hotformerloc_b200.octree import build_batch
+    cfg, depth, spec, seed, mode = CASES[name]
+    gold = np.load(os.path.join(GOLDEN, 'octree_t.npz'))
+    octree = build_batch(case_clouds(name), depth, 2, 'cuda').finalize()
+    C, d0 = 256, depth - 2
+    torch.manual_seed(14)
+    w1, b1 = torch.randn(C, 9, device=DEV) * 0.5, torch.randn(C, device=DEV) * 0.1
+    for d in (d0 - 1, d0 - 2, d0 - 3):
+        n = octree.n(d)
+        npad = int(gold[f'{name}_nnum_a_{d}'])
+        n_win = npad // K
+        tok = octree.tokens(d, npad)
+        x = torch.zeros(n_win * (K + 1), C, device=DEV)
+        feat = torch.randn(n, C, device=DEV)
+        x[_hat(n, K).to(DEV)] = feat
+        h = torch.zeros(n_win, C, device=DEV, dtype=torch.bfloat16)
+        stats = torch.zeros(n_win, 9, device=DEV)
+        _ops().rt_init(x, None, tok, n, n_win, K, C, d, 9, w1, b1, h, stats_out=stats)
+        # reference: mean over the tokens the reference's rt_init_mask keeps (padding tokens are zeros)
+        mask = np.unpackbits(gold[f'{name}_rt_init_mask_{d}'])[:n_win * K].reshape(n_win, K).astype(bool)
+        keep = torch.from_numpy(~mask).to(DEV)
+        xp = torch.cat([feat, feat.new_zeros(npad - n, C)]).view(n_win, K, C)
+        ref_rt = (xp * keep.unsqueeze(-1)).sum(1) / keep.sum(1, keepdim=True).clamp(min=1)
+        got_rt = x[::K + 1]
+        assert torch.allclose(got_rt, ref_rt, atol=1e-5, rtol=1e-5), (d, (got_rt - ref_rt).abs().max())
+        ref_stats = torch.from_numpy(gold[f'{name}_window_stats_{d}']).to(DEV)
+        assert torch.allclose(stats, ref_stats, atol=2e-5, rtol=1e-4), (d, (stats - ref_stats).abs().max())
+        ref_h = F.gelu(ref_stats @ w1.t() + b1)
+        assert torch.allclose(h.float(), ref_h, atol=3e-2, rtol=2e-2)
+
+
+def test_attn_pool_vs_torch():
+    """hfl_attn_pool (AdaptivePooling, salsa.py:25-55 restricted to each submap's tokens) against
+    softmax(q x^T / sqrt(C)) x per submap, including an EMPTY submap."""
+    torch.manual_seed(15)
+    B, K, C, kq, ktot, q_off = 5, 48, 256, 74, 128, 18
+    counts = [700, 33, 0, 1500, 259]
+    n = sum(counts)
+    n_win = -(-n // (4 * K)) * 4
+    rows = n_win * (K + 1)
+    x = torch.zeros(rows, C, device=DEV)
+    feat = torch.randn(n, C, device=DEV)
+    x[_hat(n, K).to(DEV)] = feat
+    xb = _bf(x)
+    q = torch.randn(kq, C, device=DEV)
+    npd = (kq + 63) // 64 * 64
+    qp = torch.zeros(npd, C, device=DEV, dtype=torch.bfloat16)
+    qp[:kq] = _bf(q)
+    logits = torch.empty(rows, npd, device=DEV)
+    _ops().gather_gemm(xb, qp, out_v_f32=logits)
+    tok_off = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32, device=DEV)
+    stat = torch.zeros(B, kq, 2, device=DEV)
+    out = torch.full((B, ktot, C), 7.0, device=DEV)
+    _ops().attn_pool(logits, x, xb, tok_off, stat, out, B, kq, npd, K, C, ktot, q_off, C ** -0.5)
+    fb, qb = xb.float()[_hat(n, K).to(DEV)], qp[:kq].float()
+    o = 0
+    for b, c in enumerate(counts):
+        seg = fb[o:o + c]
+        o += c
+        if c == 0:
+            assert torch.isfinite(out[b]).all()
+            continue
+        ref = ((qb @ seg.t()) * C ** -0.5).softmax(-1) @ seg
+        got = out[b, q_off:q_off + kq]
+        assert torch.allclose(got, ref, atol=2e-2, rtol=2e-2), (b, (got - ref).abs().max())
+    assert bool((out[:, :q_off] == 7.0).all()) and bool((out[:, q_off + kq:] == 7.0).all())
+
+
+@pytest.mark.parametrize('ktot,kout,od', [(128, 32, 8), (256, 64, 4)])
+def test_mixer_tail_vs_torch(ktot, kout, od):
+    """hfl_mixer_tail: channel_proj over the token axis, row_proj, flatten, L2-normalise (salsa.py:103-111)."""
+    torch.manual_seed(16)
+    B, C = 9, 256
+    x = torch.randn(B, ktot, C, device=DEV)
+    wc, bc = torch.randn(kout, ktot, device=DEV) / math.sqrt(ktot), torch.randn(kout, device=DEV) * 0.1
+    wr, br = torch.randn(od, C, device=DEV) / math.sqrt(C), torch.randn(od, device=DEV) * 0.1
+    for normalize in (True, False):
+        out = torch.zeros(B, kout * od, device=DEV)
+        _ops().mixer_tail(x, wc, bc, wr, br, out, B, ktot, kout, C, od, normalize)
+        y = F.linear(x.permute(0, 2, 1), wc, bc).permute(0, 2, 1)
+        ref = F.linear(y, wr, br).flatten(1)
+        if normalize:
+            ref = F.normalize(ref, dim=1)
+        assert torch.allclose(out, ref, atol=2e-4, rtol=1e-3), (out - ref).abs().max()
+
+
+def test_gem_pool_and_head_vs_torch():
+    """hfl_gem_pool + hfl_gem_head (PyramidOctGeMWrapper.forward, eval mode, pooling.py:87-103)."""
+    torch.manual_seed(17)
+    B, K, C, L = 4, 48, 256, 3
+    pooled = torch.zeros(B, L * C, device=DEV)
+    refs = []
+    for j, (counts, pw) in enumerate(zip(([300, 0, 77, 1000], [64, 1, 5, 200], [9, 9, 9, 9]), (3.0, 2.5, 1.7))):
+        n = sum(counts)
+        n_win = -(-max(n, 1) // (4 * K)) * 4
+        x = torch.zeros(n_win * (K + 1), C, device=DEV)
+        feat = torch.randn(n, C, device=DEV)
+        x[_hat(n, K).to(DEV)] = feat
+        tok_off = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32, device=DEV)
+        _ops().gem_pool(x, tok_off, B, K, C, pw, 1e-6, pooled, L * C, j * C)
+        t = feat.clamp(min=1e-6).pow(pw)
+        ref = torch.zeros(B, C, device=DEV)
+        o = 0
+        for b, c in enumerate(counts):
+            if c:
+                ref[b] = t[o:o + c].mean(0)
+            o += c
+        refs.append(ref.pow(1.0 / pw))
+    ref_pooled = torch.cat(refs, 1)
+    assert torch.allclose(pooled, ref_pooled, atol=1e-4, rtol=1e-3), (pooled - ref_pooled).abs().max()
+    w = torch.randn(256, L * C, device=DEV) / math.sqrt(L * C)
+    g, b, mu, var = (torch.rand(256, device=DEV) + 0.5, torch.randn(256, device=DEV) * 0.1,
+                     torch.randn(256, device=DEV) * 0.1, torch.rand(256, device=DEV) + 0.5)
+    out = torch.zeros(B, 256, device=DEV)
+    _ops().gem_head(pooled, w, g, b, mu, var, 1e-5, True, out)
+    ref = F.normalize((pooled @ w.t() - mu) / torch.sqrt(var + 1e-5) * g + b, dim=1)
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-3), (out - ref).abs().max()
+
+
+def test_hat_rows_and_remap():
+    K = 48
+    n = 1000
+    r = torch.zeros(n, device=DEV, dtype=torch.int32)
+    _ops().hat_rows(r, n, K, 5)
+    assert torch.equal(r.cpu(), (_hat(n, K) + 5).to(torch.int32))
+    src = torch.randint(-1, n, (300, 8), dtype=torch.int32)
+    out = torch.zeros_like(src, device=DEV)
+    _ops().remap_hat(src.to(DEV), out, src.numel(), K)
+    ref = torch.where(src < 0, src, (src + src // K + 1))
+    assert torch.equal(out.cpu(), ref)

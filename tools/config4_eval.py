@@ -34,48 +34,7 @@ import torch
 import torch.distributed as dist
 
 
-def write_pcd(path, xyz):
-    hdr = ('# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\n'
-           f'COUNT 1 1 1\nWIDTH {len(xyz)}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {len(xyz)}\nDATA binary\n')
-    with open(path, 'wb') as f:
-        f.write(hdr.encode())
-        f.write(np.ascontiguousarray(xyz, dtype=np.float32).tobytes())
-
-
-def make_dataset(root, runs, per_run, points, seed=11):
-    rng = np.random.default_rng(seed)
-
-    def place():          # a tilted ground plane + 12 box-shaped structures, in metres (~60 m submaps)
-        k = 12
-        ctr, half = rng.uniform(-0.8, 0.8, (k, 2)), rng.uniform(0.03, 0.15, (k, 1))
-        top, tilt = rng.uniform(0.1, 0.6, k), rng.normal(0, 0.1, 2)
-        n_obj = points // 2
-        xy_g = rng.uniform(-0.95, 0.95, (points - n_obj, 2))
-        z_g = -0.3 + xy_g @ tilt + rng.normal(0, 0.01, len(xy_g))
-        which = rng.integers(0, k, n_obj)
-        xy_o = ctr[which] + rng.uniform(-1, 1, (n_obj, 2)) * half[which]
-        z_o = -0.3 + xy_o @ tilt + rng.uniform(0, 1, n_obj) * top[which]
-        pts = np.concatenate([np.concatenate([xy_g, xy_o]), np.concatenate([z_g, z_o])[:, None]], 1)
-        return np.clip(pts, -1, 1) * 30.0
-    places = [place() for _ in range(per_run)]
-    sets = []
-    for r in range(runs):
-        d = os.path.join(root, 'Venman', f'run{r}', 'Clouds')
-        os.makedirs(d, exist_ok=True)
-        s = {}
-        for i, base in enumerate(places):
-            yaw = rng.normal(0, 0.03)
-            c, sn = np.cos(yaw), np.sin(yaw)
-            keep = rng.random(len(base)) > 0.1
-            pts = base[keep] + rng.normal(0, 0.05, (int(keep.sum()), 3))
-            pts = pts @ np.array([[c, -sn, 0], [sn, c, 0], [0, 0, 1]]).T
-            rel = os.path.join('Venman', f'run{r}', 'Clouds', f'{i:06d}.pcd')
-            write_pcd(os.path.join(root, rel), pts)
-            s[i] = {'query': rel, 'northing': float(3.0 * i), 'easting': float(0.5 * r)}
-            for m in range(runs):                       # the true neighbour: the same place in the other runs
-                s[i][m] = [i] if m != r else []
-        sets.append(s)
-    return sets
+from hotformerloc_b200.datasets.synthetic import make_eval_dataset as make_dataset  # noqa: E402
 
 
 def main():
