@@ -5,9 +5,11 @@
 // (N_win,K,K) masks or the (N_win,K,K,3) rel-pos tensors of the reference
 // (models/octree.py:193-209, 272-283): the batch mask and the RPE index are computed
 // from a per-token (x,y,z,submap) int16x4 table.
-//   k_window_attn3: octree window attention, plain / dilated / hierarchical (+relay token) -- the
-//                   default: pair bias summed once per 8 heads into a fragment-ordered smem table
-//                   (k_window_attn2 / k_window_attn are the earlier designs, HFL_ATTN_V=2 / 1)
+//   k_window_attn3: stand-alone octree window attention on mma.sync for the window shapes the fused
+//                   tcgen05 kernel (attn_fused.cu) does not take (K + relay token > 64: the K = 64
+//                   hierarchical levels of the CS-Wild-Places / Campus3D cfgs, K = 96 sweeps), and the
+//                   A/B reference of the fused path (HFL_FUSED_ATTN=0): pair bias summed once per 8 heads
+//                   into a fragment-ordered smem table
 //   k_varlen_attn : relay-token self-attention over ragged per-submap sequences
 // qkv is the bf16 output of the tcgen05 projection GEMM, laid out [row, 3C] as
 // [q | k | v] x [head, 16]  (octformer_backbone.py:71-72).
@@ -19,7 +21,7 @@
 namespace hfl {
 
 constexpr int AT_HD = 16;
-constexpr int AT_NT = 10;              // score n-tiles (8 keys each) -> up to 80 keys per pass
+constexpr int AT_NT = 13;              // score n-tiles (8 keys each) -> up to 104 keys per pass (K = 96 + relay token)
 constexpr int AT_KEYS = AT_NT * 8;
 constexpr int AT_RS = 48;              // smem row stride in bytes (16 bf16 + pad, conflict-free): ragged kernel
 constexpr int AT_ROW = 32;             // window kernel: unpadded 16 x bf16 rows, halves swizzled
@@ -60,279 +62,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// CTA = one window, warp = one head.  Per window the CTA builds, once for all heads, a
-// packed table  code[row][key] = 10-bit byte offsets into the (x | y | z) RPE sub-tables; every
-// sub-table ends with a zero slot (pairs without RPE) and the x table with a -inf slot that
-// masked pairs (different submap / padding key) point at, so masking costs no compare/select.
-// Each warp then runs QK^T -> +bias -> softmax -> PV for its head with 3 LDS + 4 integer ops +
-// 3 FP ops of bias work per score; the softmax row sums come out of the PV MMA (a ones column).
-// With relay tokens the K window tokens form K/16 query tiles and the single relay-token
-// query row is handled by a short CUDA-core path instead of a 1/16-full MMA tile.
-template <int NT>
-__global__ void __launch_bounds__(512, 1) k_window_attn(const WinAttnParams p) {
-  constexpr int NTC = NT * 8;          // key columns covered
-  constexpr int PITCH = NTC + 4;       // code row pitch (words)
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
-  const int g = lane >> 2, t = lane & 3;
-  const int K = p.K, hat = p.hat, L = K + hat;
-  const int num = 2 * p.bnd + 1, sub = num + 2;          // sub-table pitch incl. the zero and -inf slots
-  float* s_rpe = reinterpret_cast<float*>(smem);                       // [H][3*sub]
-  const int rpe_bytes = (p.H * 3 * sub * 4 + 15) & ~15;
-  uint32_t* s_code = reinterpret_cast<uint32_t*>(smem + rpe_bytes);    // [K+1][PITCH]
-  const int code_bytes = ((K + 1) * PITCH * 4 + 15) & ~15;
-  short4* s_tok = reinterpret_cast<short4*>(smem + rpe_bytes + code_bytes);   // [2][NTC]
-  float* s_prob = reinterpret_cast<float*>(smem + rpe_bytes + code_bytes + 2 * NTC * 8);  // [H][NTC]
-  // K and V of this warp's head: [2 windows in flight][K | V][NTC rows x 32 B]; the 16-byte
-  // halves of rows 4-7 of every 8 are swapped, which makes the fragment loads, ldmatrix and the
-  // 16-byte cp.async stores conflict-free without padding the rows to 48 B
-  const uint32_t kv_base = (uint32_t)(rpe_bytes + code_bytes + 2 * NTC * 8 + p.H * NTC * 4);
-  const uint32_t smem_u = ptx::smem_u32(smem);
-  uint8_t* wbase = smem + kv_base + (size_t)warp * (4 * NTC * AT_ROW);
-  auto kv_off = [](int row, int half) -> uint32_t {
-    return (uint32_t)row * AT_ROW + (uint32_t)((half ^ ((row >> 2) & 1)) << 4);
-  };
-
-  for (int i = threadIdx.x; i < p.H * 3 * sub; i += blockDim.x) {
-    const int h = i / (3 * sub), e = i - h * 3 * sub;
-    const int axis = e / sub, k = e - axis * sub;
-    float v = 0.f;
-    if (k < num) v = p.rpe ? __ldg(p.rpe + (size_t)(axis * num + k) * p.H + h) * LOG2E : 0.f;
-    else if (k == num + 1 && axis == 0) v = -INFINITY;
-    s_rpe[i] = v;
-  }
-  for (int i = threadIdx.x; i < 2 * NTC; i += blockDim.x)       // padding keys never match a submap
-    if ((i % NTC) >= L) s_tok[i] = make_short4(0, 0, 0, -2);
-  const int h = warp;
-  const float* tabx = s_rpe + h * 3 * sub;
-  const float* taby = tabx + sub;
-  const float* tabz = taby + sub;
-  const int C3 = 3 * p.C;
-  const float sc = p.scale * LOG2E;
-  const uint32_t zero_off = (uint32_t)num * 4u;
-  const uint32_t MASKED = ((uint32_t)(num + 1) * 4u) | (zero_off << 10) | (zero_off << 20);
-  const int n_mt = K / 16;
-
-  // stage window w (token table for the CTA, K / V of this warp's head) into buffer `buf`
-  auto stage_window = [&](int w, int buf) {
-    for (int s = threadIdx.x; s < L; s += blockDim.x) {
-      int64_t row, tok;
-      slot_row(p, w, s, row, tok);
-      ptx::cp_async8(ptx::smem_u32(s_tok + buf * NTC + s), p.xyzb + (tok >= 0 ? tok : (int64_t)w * K));  // relay token: id of the first token
-    }
-    // K and V of ALL heads, cooperatively: consecutive threads fetch consecutive 16-byte pieces of one
-    // row (2H pieces = the row's K or V of every head, contiguous in qkv), so one warp instruction
-    // touches 4 cache lines instead of 32, and drop them into the owning head's (warp's) buffer
-    const int pieces = 2 * p.H;
-    for (int i = threadIdx.x; i < 2 * NTC * pieces; i += blockDim.x) {
-      const int piece = i % pieces, rest = i / pieces;
-      const int s = rest % NTC, which = rest / NTC;                  // 0 = K, 1 = V
-      const int hd = piece >> 1, half = piece & 1;
-      int64_t row = 0, tok;
-      const bool ok = s < L;
-      if (ok) slot_row(p, w, s, row, tok);
-      const __nv_bfloat16* src = p.qkv + row * C3 + (which + 1) * p.C + piece * 8;
-      const uint32_t dst = smem_u + kv_base + (uint32_t)hd * (4 * NTC * AT_ROW) +
-                           (uint32_t)buf * (2 * NTC * AT_ROW) + (uint32_t)which * (NTC * AT_ROW) + kv_off(s, half);
-      ptx::cp_async16(dst, src, ok ? 16u : 0u);
-    }
-    ptx::cp_async_commit();
-  };
-  auto load_q = [&](int w, int mt, uint32_t (&q)[4], int64_t& row0, int64_t& row1) {
-    int64_t tk_;
-    slot_row(p, w, mt * 16 + g + hat, row0, tk_);
-    slot_row(p, w, mt * 16 + g + 8 + hat, row1, tk_);
-    const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
-    const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
-    q[0] = __ldg(q0 + t); q[2] = __ldg(q0 + t + 4);
-    q[1] = __ldg(q1 + t); q[3] = __ldg(q1 + t + 4);
-  };
-
-  // Software pipeline over this CTA's windows: the loads of window w + 1 are in flight while the
-  // mask/RPE code table of window w is built and its attention is computed (one CTA per SM, so
-  // nothing else would hide the global-memory latency).
-  if ((int)blockIdx.x < p.n_win) stage_window(blockIdx.x, 0);
-  int buf = 0;
-  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x, buf ^= 1) {
-    ptx::cp_async_wait<0>();
-    __syncthreads();                              // window w staged; window w - 1 fully consumed
-    if (w + (int)gridDim.x < p.n_win) stage_window(w + gridDim.x, buf ^ 1);
-    uint32_t qn[4];                               // Q fragment of the next query tile (prefetched)
-    int64_t row0n, row1n;
-    load_q(w, 0, qn, row0n, row1n);
-    const short4* tokw = s_tok + buf * NTC;
-    const uint8_t* sK = wbase + (size_t)buf * (2 * NTC * AT_ROW);
-    const uint8_t* sV = sK + NTC * AT_ROW;
-    const uint32_t sV_u = ptx::smem_u32(sV);
-    // ---- packed mask / RPE-offset table: rows 0..K-1 = window tokens, row K = relay token ----
-    for (int e = threadIdx.x; e < (K + hat) * NTC; e += blockDim.x) {
-      const int r = e / NTC, j = e - r * NTC;
-      const bool rt_row = r == K;
-      const short4 ti = tokw[rt_row ? 0 : r + hat];
-      const short4 tj = tokw[j];
-      uint32_t code = MASKED;
-      if (j < L && ti.w == tj.w) {
-        if (rt_row || (hat && j == 0) || !p.rpe) {
-          code = zero_off | (zero_off << 10) | (zero_off << 20);
-        } else {
-          const uint32_t ox = (uint32_t)(min(max((int)ti.x - (int)tj.x, -p.bnd), p.bnd) + p.bnd) * 4u;
-          const uint32_t oy = (uint32_t)(min(max((int)ti.y - (int)tj.y, -p.bnd), p.bnd) + p.bnd) * 4u;
-          const uint32_t oz = (uint32_t)(min(max((int)ti.z - (int)tj.z, -p.bnd), p.bnd) + p.bnd) * 4u;
-          code = ox | (oy << 10) | (oz << 20);
-        }
-      }
-      s_code[r * PITCH + j] = code;
-    }
-    __syncthreads();
-
-    // ---- K/16 query tiles of window tokens ----
-    const uint8_t* tx = reinterpret_cast<const uint8_t*>(tabx);
-    const uint8_t* ty = reinterpret_cast<const uint8_t*>(taby);
-    const uint8_t* tz = reinterpret_cast<const uint8_t*>(tabz);
-    for (int mt = 0; mt < n_mt; ++mt) {
-      const int r0 = mt * 16 + g, r1 = r0 + 8;               // token rows (slots r + hat)
-      const int64_t row0 = row0n, row1 = row1n;
-      const uint32_t qa[4] = {qn[0], qn[1], qn[2], qn[3]};
-      if (mt + 1 < n_mt) load_q(w, mt + 1, qn, row0n, row1n);
-      float s[NT][4];
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        uint32_t kb[2];
-        kb[0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
-        kb[1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
-        ptx::mma16816(s[nt], qa, kb);
-        const uint2 c0 = *reinterpret_cast<const uint2*>(s_code + r0 * PITCH + nt * 8 + 2 * t);
-        const uint2 c1 = *reinterpret_cast<const uint2*>(s_code + r1 * PITCH + nt * 8 + 2 * t);
-        const uint32_t cc[4] = {c0.x, c0.y, c1.x, c1.y};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t c = cc[e];
-          const float bx = *reinterpret_cast<const float*>(tx + (c & 1023u));      // -inf for a masked pair
-          const float by = *reinterpret_cast<const float*>(ty + ((c >> 10) & 1023u));
-          const float bz = *reinterpret_cast<const float*>(tz + (c >> 20));
-          s[nt][e] = fmaf(s[nt][e], sc, bx) + (by + bz);
-        }
-        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      // P = 2^(s - max) rounded to bf16; O and the row sums l both come from the PV MMAs (V gets a
-      // virtual all-ones column), so the normalisation uses exactly the probabilities that were summed
-      float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t ones[2] = {0x3F803F80u, 0x3F803F80u};
-#pragma unroll
-      for (int kt = 0; kt < (NT + 1) / 2; ++kt) {
-        uint32_t pa[4];
-        pa[0] = pack_bf16(fast_exp2(s[2 * kt][0] - mx0), fast_exp2(s[2 * kt][1] - mx0));
-        pa[1] = pack_bf16(fast_exp2(s[2 * kt][2] - mx1), fast_exp2(s[2 * kt][3] - mx1));
-        if (2 * kt + 1 < NT) {
-          pa[2] = pack_bf16(fast_exp2(s[2 * kt + 1][0] - mx0), fast_exp2(s[2 * kt + 1][1] - mx0));
-          pa[3] = pack_bf16(fast_exp2(s[2 * kt + 1][2] - mx1), fast_exp2(s[2 * kt + 1][3] - mx1));
-        } else {
-          pa[2] = pa[3] = 0u;
-        }
-        uint32_t vb[4];
-        const int mi = lane >> 3;
-        int key = kt * 16 + (mi & 1) * 8 + (lane & 7);
-        key = key < NTC ? key : 0;                  // second half of an odd last tile: P == 0
-        ptx::ldmatrix_x4_trans(vb, sV_u + kv_off(key, mi >> 1));
-        uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
-        ptx::mma16816(o[0], pa, b0);
-        ptx::mma16816(o[1], pa, b1);
-        ptx::mma16816(ls, pa, ones);
-      }
-      // every row has at least itself unmasked, so l > 0
-      const float i0 = 1.f / ls[0], i1 = 1.f / ls[2];
-      uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
-      uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
-      d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
-      d0[t + 4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
-      d1[t] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
-      d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
-    }
-    // ---- the relay-token query row (no RPE): lanes over keys, then lanes over (dim, half) ----
-    if (hat) {
-      const int64_t rowq = (int64_t)w * (K + 1);
-      float q[AT_HD];
-      {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + rowq * C3 + h * AT_HD);
-        const uint4 a = __ldg(qp), b = __ldg(qp + 1);
-        const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
-          q[2 * i] = f.x; q[2 * i + 1] = f.y;
-        }
-      }
-      float sj[(NTC + 31) / 32];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int u = 0; u < (NTC + 31) / 32; ++u) {
-        const int j = lane + 32 * u;
-        float a = -INFINITY;
-        if (j < NTC && s_code[K * PITCH + j] != MASKED) {
-          const uint4 ka = *reinterpret_cast<const uint4*>(sK + kv_off(j, 0));
-          const uint4 kb = *reinterpret_cast<const uint4*>(sK + kv_off(j, 1));
-          const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-          a = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
-            a = fmaf(q[2 * i], f.x, a);
-            a = fmaf(q[2 * i + 1], f.y, a);
-          }
-          a *= sc;
-        }
-        sj[u] = a;
-        mx = fmaxf(mx, a);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float l = 0.f;
-      float* pr = s_prob + h * NTC;
-#pragma unroll
-      for (int u = 0; u < (NTC + 31) / 32; ++u) {
-        const int j = lane + 32 * u;
-        const float e = fast_exp2(sj[u] - mx);
-        l += e;
-        if (j < NTC) pr[j] = e;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-      __syncwarp();
-      const int d = lane & 15, half = lane >> 4;
-      float acc4[4] = {0.f, 0.f, 0.f, 0.f};                    // independent chains hide the LDS latency
-      const uint8_t* vcol = sV + (d & 7) * 2;
-#pragma unroll 2
-      for (int j0 = half; j0 < NTC; j0 += 8) {                 // padding keys: pr == 0, V == 0
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + 2 * u;
-          acc4[u] = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vcol + kv_off(j, d >> 3))), acc4[u]);
-        }
-      }
-      float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-      if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Two heads per warp.  The per-score loop of k_window_attn is bound by shared-memory (LSU) wavefronts,
-// three quarters of which are the RPE table look-ups (ncu source page: 41 % stall_mio).  Here the
-// tables hold fp16 PAIRS -- one 32-bit entry carries the (log2e-scaled) bias of heads 2w and 2w+1 --
-// so one look-up serves two heads: warp w handles head 2w fully (QK^T, bias, softmax, PV) while it
-// stashes the other head's summed bias (2 fp16 per register), then replays head 2w+1 from the stash.
-// 8 warps per window (H = 16), two CTAs (windows) per SM instead of a software pipeline.
-// fp16 tables: |bias error| <= 2^-11 relative per term, well below the bf16 rounding of P.
-// ---------------------------------------------------------------------------
+// ---- fp16 pair helpers ----
 __device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
   uint32_t d;
   asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -354,273 +84,16 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return d;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(256, 2) k_window_attn2(const WinAttnParams p) {
-  constexpr int NTC = NT * 8;
-  constexpr int PITCH = NTC + 4;
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int K = p.K, hat = p.hat, L = K + hat;
-  const int num = 2 * p.bnd + 1, sub = num + 2;
-  const int HP = p.H >> 1;                                                // head pairs = warps
-  uint32_t* s_rpe = reinterpret_cast<uint32_t*>(smem);                    // [HP][3][sub] fp16x2
-  const int rpe_bytes = (HP * 3 * sub * 4 + 15) & ~15;
-  uint32_t* s_code = reinterpret_cast<uint32_t*>(smem + rpe_bytes);       // [K+1][PITCH]
-  const int code_bytes = ((K + 1) * PITCH * 4 + 15) & ~15;
-  short4* s_tok = reinterpret_cast<short4*>(smem + rpe_bytes + code_bytes);            // [NTC]
-  float* s_prob = reinterpret_cast<float*>(smem + rpe_bytes + code_bytes + NTC * 8);  // [H][NTC]
-  const uint32_t kv_base = (uint32_t)(rpe_bytes + code_bytes + NTC * 8 + p.H * NTC * 4);   // [H][K | V][NTC x 32 B]
-  const uint32_t smem_u = ptx::smem_u32(smem);
-  auto kv_off = [](int row, int half) -> uint32_t {
-    return (uint32_t)row * AT_ROW + (uint32_t)((half ^ ((row >> 2) & 1)) << 4);
-  };
-
-  for (int i = threadIdx.x; i < HP * 3 * sub; i += blockDim.x) {
-    const int hp = i / (3 * sub), e = i - hp * 3 * sub;
-    const int axis = e / sub, k = e - axis * sub;
-    float a = 0.f, b = 0.f;
-    if (k < num) {
-      if (p.rpe) {
-        a = __ldg(p.rpe + (size_t)(axis * num + k) * p.H + 2 * hp) * LOG2E;
-        b = __ldg(p.rpe + (size_t)(axis * num + k) * p.H + 2 * hp + 1) * LOG2E;
-      }
-    } else if (k == num + 1 && axis == 0) {
-      a = b = -INFINITY;
-    }
-    s_rpe[i] = pack_h2(a, b);
-  }
-  for (int i = threadIdx.x; i < NTC; i += blockDim.x)
-    if (i >= L) s_tok[i] = make_short4(0, 0, 0, -2);
-  const uint8_t* tx = reinterpret_cast<const uint8_t*>(s_rpe + warp * 3 * sub);
-  const uint8_t* ty = tx + sub * 4;
-  const uint8_t* tz = ty + sub * 4;
-  const int C3 = 3 * p.C;
-  const float sc = p.scale * LOG2E;
-  const uint32_t zero_off = (uint32_t)num * 4u;
-  const uint32_t MASKED = ((uint32_t)(num + 1) * 4u) | (zero_off << 10) | (zero_off << 20);
-  const int n_mt = K / 16;
-  const uint32_t ones[2] = {0x3F803F80u, 0x3F803F80u};
-
-  for (int w = blockIdx.x; w < p.n_win; w += gridDim.x) {
-    __syncthreads();                              // previous window fully consumed
-    for (int sl = threadIdx.x; sl < L; sl += blockDim.x) {
-      int64_t row, tok;
-      slot_row(p, w, sl, row, tok);
-      ptx::cp_async8(ptx::smem_u32(s_tok + sl), p.xyzb + (tok >= 0 ? tok : (int64_t)w * K));
-    }
-    {
-      const int pieces = 2 * p.H;
-      for (int i = threadIdx.x; i < 2 * NTC * pieces; i += blockDim.x) {
-        const int piece = i % pieces, rest = i / pieces;
-        const int sl = rest % NTC, which = rest / NTC;               // 0 = K, 1 = V
-        const int hd = piece >> 1, half = piece & 1;
-        int64_t row = 0, tok;
-        const bool ok = sl < L;
-        if (ok) slot_row(p, w, sl, row, tok);
-        const __nv_bfloat16* src = p.qkv + row * C3 + (which + 1) * p.C + piece * 8;
-        const uint32_t dst = smem_u + kv_base + (uint32_t)hd * (2 * NTC * AT_ROW) +
-                             (uint32_t)which * (NTC * AT_ROW) + kv_off(sl, half);
-        ptx::cp_async16(dst, src, ok ? 16u : 0u);
-      }
-    }
-    ptx::cp_async_commit();
-    ptx::cp_async_wait<0>();
-    __syncthreads();
-    // ---- packed mask / RPE-offset table (shared by all heads) ----
-    for (int e = threadIdx.x; e < (K + hat) * NTC; e += blockDim.x) {
-      const int r = e / NTC, j = e - r * NTC;
-      const bool rt_row = r == K;
-      const short4 ti = s_tok[rt_row ? 0 : r + hat];
-      const short4 tj = s_tok[j];
-      uint32_t code = MASKED;
-      if (j < L && ti.w == tj.w) {
-        if (rt_row || (hat && j == 0) || !p.rpe) {
-          code = zero_off | (zero_off << 10) | (zero_off << 20);
-        } else {
-          const uint32_t ox = (uint32_t)(min(max((int)ti.x - (int)tj.x, -p.bnd), p.bnd) + p.bnd) * 4u;
-          const uint32_t oy = (uint32_t)(min(max((int)ti.y - (int)tj.y, -p.bnd), p.bnd) + p.bnd) * 4u;
-          const uint32_t oz = (uint32_t)(min(max((int)ti.z - (int)tj.z, -p.bnd), p.bnd) + p.bnd) * 4u;
-          code = ox | (oy << 10) | (oz << 20);
-        }
-      }
-      s_code[r * PITCH + j] = code;
-    }
-    __syncthreads();
-
-    // ---- K/16 query tiles; per tile head 2w (with the look-ups), then head 2w+1 (from the stash) ----
-    for (int mt = 0; mt < n_mt; ++mt) {
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
-      int64_t row0, row1, tk_;
-      slot_row(p, w, r0 + hat, row0, tk_);
-      slot_row(p, w, r1 + hat, row1, tk_);
-      uint32_t stash[NT][2];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int h = 2 * warp + hh;
-        const uint8_t* sK = smem + kv_base + (size_t)h * (2 * NTC * AT_ROW);
-        const uint32_t sV_u = smem_u + kv_base + (uint32_t)h * (2 * NTC * AT_ROW) + NTC * AT_ROW;
-        uint32_t qa[4];
-        {
-          const uint32_t* q0 = reinterpret_cast<const uint32_t*>(p.qkv + row0 * C3 + h * AT_HD);
-          const uint32_t* q1 = reinterpret_cast<const uint32_t*>(p.qkv + row1 * C3 + h * AT_HD);
-          qa[0] = __ldg(q0 + t); qa[2] = __ldg(q0 + t + 4);
-          qa[1] = __ldg(q1 + t); qa[3] = __ldg(q1 + t + 4);
-        }
-        float s[NT][4];
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-          uint32_t kb[2];
-          kb[0] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 0) + t * 4);
-          kb[1] = *reinterpret_cast<const uint32_t*>(sK + kv_off(nt * 8 + g, 1) + t * 4);
-          ptx::mma16816(s[nt], qa, kb);
-          if (hh == 0) {
-            const uint2 c0 = *reinterpret_cast<const uint2*>(s_code + r0 * PITCH + nt * 8 + 2 * t);
-            const uint2 c1 = *reinterpret_cast<const uint2*>(s_code + r1 * PITCH + nt * 8 + 2 * t);
-            const uint32_t cc[4] = {c0.x, c0.y, c1.x, c1.y};
-            uint32_t sum[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t c = cc[e];
-              const uint32_t bx = *reinterpret_cast<const uint32_t*>(tx + (c & 1023u));   // (-inf, -inf) if masked
-              const uint32_t by = *reinterpret_cast<const uint32_t*>(ty + ((c >> 10) & 1023u));
-              const uint32_t bz = *reinterpret_cast<const uint32_t*>(tz + (c >> 20));
-              sum[e] = hadd2_u32(hadd2_u32(by, bz), bx);
-              s[nt][e] = fmaf(s[nt][e], sc, h_lo(sum[e]));
-            }
-            stash[nt][0] = __byte_perm(sum[0], sum[1], 0x7632);     // head 2w+1: (e0, e1)
-            stash[nt][1] = __byte_perm(sum[2], sum[3], 0x7632);     //            (e2, e3)
-          } else {
-            s[nt][0] = fmaf(s[nt][0], sc, h_lo(stash[nt][0]));
-            s[nt][1] = fmaf(s[nt][1], sc, h_hi(stash[nt][0]));
-            s[nt][2] = fmaf(s[nt][2], sc, h_lo(stash[nt][1]));
-            s[nt][3] = fmaf(s[nt][3], sc, h_hi(stash[nt][1]));
-          }
-          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int kt = 0; kt < (NT + 1) / 2; ++kt) {
-          uint32_t pa[4];
-          pa[0] = pack_bf16(fast_exp2(s[2 * kt][0] - mx0), fast_exp2(s[2 * kt][1] - mx0));
-          pa[1] = pack_bf16(fast_exp2(s[2 * kt][2] - mx1), fast_exp2(s[2 * kt][3] - mx1));
-          if (2 * kt + 1 < NT) {
-            pa[2] = pack_bf16(fast_exp2(s[2 * kt + 1][0] - mx0), fast_exp2(s[2 * kt + 1][1] - mx0));
-            pa[3] = pack_bf16(fast_exp2(s[2 * kt + 1][2] - mx1), fast_exp2(s[2 * kt + 1][3] - mx1));
-          } else {
-            pa[2] = pa[3] = 0u;
-          }
-          uint32_t vb[4];
-          const int mi = lane >> 3;
-          int key = kt * 16 + (mi & 1) * 8 + (lane & 7);
-          key = key < NTC ? key : 0;
-          ptx::ldmatrix_x4_trans(vb, sV_u + kv_off(key, mi >> 1));
-          uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
-          ptx::mma16816(o[0], pa, b0);
-          ptx::mma16816(o[1], pa, b1);
-          ptx::mma16816(ls, pa, ones);
-        }
-        const float i0 = 1.f / ls[0], i1 = 1.f / ls[2];
-        uint32_t* d0 = reinterpret_cast<uint32_t*>(p.out + row0 * p.C + h * AT_HD);
-        uint32_t* d1 = reinterpret_cast<uint32_t*>(p.out + row1 * p.C + h * AT_HD);
-        d0[t] = pack_bf16(o[0][0] * i0, o[0][1] * i0);
-        d0[t + 4] = pack_bf16(o[1][0] * i0, o[1][1] * i0);
-        d1[t] = pack_bf16(o[0][2] * i1, o[0][3] * i1);
-        d1[t + 4] = pack_bf16(o[1][2] * i1, o[1][3] * i1);
-      }
-    }
-    // ---- the relay-token query row of both heads (no RPE): lanes over keys, then over (dim, half) ----
-    if (hat) {
-      const int64_t rowq = (int64_t)w * (K + 1);
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        const int h = 2 * warp + hh;
-        const uint8_t* sK = smem + kv_base + (size_t)h * (2 * NTC * AT_ROW);
-        const uint8_t* sV = sK + NTC * AT_ROW;
-        float q[AT_HD];
-        {
-          const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + rowq * C3 + h * AT_HD);
-          const uint4 a = __ldg(qp), b = __ldg(qp + 1);
-          const uint32_t wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
-            q[2 * i] = f.x; q[2 * i + 1] = f.y;
-          }
-        }
-        float sj[(NTC + 31) / 32];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int u = 0; u < (NTC + 31) / 32; ++u) {
-          const int j = lane + 32 * u;
-          float a = -INFINITY;
-          if (j < NTC && s_code[K * PITCH + j] != MASKED) {
-            const uint4 ka = *reinterpret_cast<const uint4*>(sK + kv_off(j, 0));
-            const uint4 kb = *reinterpret_cast<const uint4*>(sK + kv_off(j, 1));
-            const uint32_t wds[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
-            a = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
-              a = fmaf(q[2 * i], f.x, a);
-              a = fmaf(q[2 * i + 1], f.y, a);
-            }
-            a *= sc;
-          }
-          sj[u] = a;
-          mx = fmaxf(mx, a);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float l = 0.f;
-        float* pr = s_prob + h * NTC;
-#pragma unroll
-        for (int u = 0; u < (NTC + 31) / 32; ++u) {
-          const int j = lane + 32 * u;
-          const float e = fast_exp2(sj[u] - mx);
-          l += e;
-          if (j < NTC) pr[j] = e;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-        __syncwarp();
-        const int d = lane & 15, half = lane >> 4;
-        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint8_t* vcol = sV + (d & 7) * 2;
-#pragma unroll 2
-        for (int j0 = half; j0 < NTC; j0 += 8) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = j0 + 2 * u;
-            acc4[u] = fmaf(pr[j], __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(vcol + kv_off(j, d >> 3))), acc4[u]);
-          }
-        }
-        float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (half == 0) p.out[rowq * p.C + h * AT_HD + d] = __float2bfloat16(acc / l);
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
 // v3: the bias of one (query, key) pair is summed ONCE for eight heads and parked in shared memory.
-// k_window_attn2 spends ~20 thread-instructions per score, half of them on the bias: three field
+// A per-head design spends ~20 thread-instructions per score, half of them on the bias: three field
 // extractions + three table look-ups per pair and pair of heads, repeated by every warp.  Here a
 // build phase walks the pairs of the window once per group of 8 heads: the RPE tables hold one
 // 16-byte entry (8 x fp16, one per head) per offset, so 3 LDS.128 + 8 HADD2 give the bias of a pair for
 // all 8 heads; the sums are written in MMA-fragment order ([head][m-tile][n-tile][lane] -> 4 fp16 =
 // this lane's four scores), so the score loop of a warp (= one head) costs ONE conflict-free LDS.64
 // + 4 converts per score tile.  Masked pairs (other submap / padding key) get -inf for all heads,
-// pairs without RPE (relay-token key, disable_RPE) the zero slot -- same table convention as v2.
+// pairs without RPE (relay-token key, disable_RPE) the zero slot.
 // H = 16 runs as two passes of 8 heads (K/V of 8 heads staged per pass): ~80 KB of shared memory per
 // window at K = 48, two windows per SM.
 // ---------------------------------------------------------------------------
@@ -631,8 +104,8 @@ __device__ __forceinline__ uint4 hadd2_x4(const uint4 a, const uint4 b) {
 struct Win3Smem {            // byte offsets into dynamic shared memory
   int rpe, tok, rtm, prob, bias, kv, total;
 };
-// compact (experimental 3-CTAs-per-SM variant): only the current pass's RPE table is resident and the
-// relay-token probabilities reuse the warp's own (finished) bias slice
+// compact: only the current pass's RPE table is resident and the relay-token probabilities reuse the
+// warp's own (finished) bias slice -- for windows whose full layout exceeds the shared memory (K = 96 + relay token)
 __host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd, bool compact = false) {
   const int L = K + hat, NT = (L + 7) / 8, NTC = NT * 8, sub = 2 * bnd + 3, passes = H / 8;
   Win3Smem m;
@@ -650,12 +123,10 @@ __host__ __device__ inline Win3Smem win3_layout(int H, int K, int hat, int bnd, 
 
 // WPH = warps per head: 1 -> 8 warps, two windows per SM; 2 -> 16 warps sharing a head's query tiles,
 // for windows whose tables allow only one CTA per SM (K = 64: 123 KB)
-// CPS = CTAs per SM the kernel is compiled for: 3 (experimental, HFL_ATTN_CTAS=3, WPH = 1 only) caps the
-// registers at 80 (no spills at NT = 7) and uses the compact shared-memory layout (74 KB at K = 48, H = 16);
-// compiled but NOT yet measured on a B200 (DESIGN.md round-2 plan item 3)
-template <int NT, int WPH, int CPS = 2>
-__global__ void __launch_bounds__(256 * WPH, WPH == 1 ? CPS : 1) k_window_attn3(const WinAttnParams p) {
-  constexpr bool COMPACT = CPS == 3;
+// (a three-windows-per-SM instantiation, 80 registers + compact tables, was measured in round 2: 28.0 vs
+// 25.9 ms per step -- slower, removed)
+template <int NT, int WPH, bool COMPACT = false>
+__global__ void __launch_bounds__(256 * WPH, WPH == 1 ? 2 : 1) k_window_attn3(const WinAttnParams p) {
   constexpr int NTC = NT * 8;
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp_id = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -982,13 +453,15 @@ struct VarAttnParams {
   int B, H, C;
   float scale;
 };
+constexpr int VA_NT = 10;       // key tiles per block of the ragged kernel (even: the P.V loop takes pairs)
+constexpr int VA_KEYS = VA_NT * 8;
 constexpr int VA_WARPS = 4;
 constexpr int VA_MT = 4;        // m-tiles per warp -> 256 query rows per CTA
 
 __global__ void __launch_bounds__(VA_WARPS * 32) k_varlen_attn(const VarAttnParams p) {
-  __shared__ __align__(16) uint8_t sK[AT_KEYS * AT_RS];
-  __shared__ __align__(16) uint8_t sV[AT_KEYS * AT_RS];
-  __shared__ int32_t sId[AT_KEYS];
+  __shared__ __align__(16) uint8_t sK[VA_KEYS * AT_RS];
+  __shared__ __align__(16) uint8_t sV[VA_KEYS * AT_RS];
+  __shared__ int32_t sId[VA_KEYS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.x, h = blockIdx.y;
@@ -1025,9 +498,9 @@ __global__ void __launch_bounds__(VA_WARPS * 32) k_varlen_attn(const VarAttnPara
       for (int c = 0; c < 4; ++c) o[u][a][c] = 0.f;
   }
 
-  for (int kb0 = 0; kb0 < L; kb0 += AT_KEYS) {
+  for (int kb0 = 0; kb0 < L; kb0 += VA_KEYS) {
     __syncthreads();
-    for (int s = threadIdx.x; s < AT_KEYS; s += blockDim.x) {
+    for (int s = threadIdx.x; s < VA_KEYS; s += blockDim.x) {
       const bool ok = kb0 + s < L;
       const __nv_bfloat16* src = p.qkv + (int64_t)(beg + (ok ? kb0 + s : 0)) * C3 + p.C + h * AT_HD;
       ptx::cp_async16(sK_u + s * AT_RS, src, ok ? 16u : 0u);
@@ -1042,10 +515,10 @@ __global__ void __launch_bounds__(VA_WARPS * 32) k_varlen_attn(const VarAttnPara
 #pragma unroll
     for (int u = 0; u < VA_MT; ++u) {
       if (q0 + (warp * VA_MT + u) * 16 >= L) continue;        // warp-uniform
-      float s[AT_NT][4];
+      float s[VA_NT][4];
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < AT_NT; ++nt) {
+      for (int nt = 0; nt < VA_NT; ++nt) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
         uint32_t kb[2];
         const uint8_t* kr = sK + (nt * 8 + g) * AT_RS + t * 4;
@@ -1071,7 +544,7 @@ __global__ void __launch_bounds__(VA_WARPS * 32) k_varlen_attn(const VarAttnPara
       m0[u] = n0; m1[u] = n1;
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < AT_NT; ++nt) {
+      for (int nt = 0; nt < VA_NT; ++nt) {
         s[nt][0] = exp2f(s[nt][0] - e0); s[nt][1] = exp2f(s[nt][1] - e0);
         s[nt][2] = exp2f(s[nt][2] - e1); s[nt][3] = exp2f(s[nt][3] - e1);
         a0 += s[nt][0] + s[nt][1];
@@ -1086,7 +559,7 @@ __global__ void __launch_bounds__(VA_WARPS * 32) k_varlen_attn(const VarAttnPara
         o[u][a][0] *= c0; o[u][a][1] *= c0; o[u][a][2] *= c1; o[u][a][3] *= c1;
       }
 #pragma unroll
-      for (int kt = 0; kt < AT_NT / 2; ++kt) {
+      for (int kt = 0; kt < VA_NT / 2; ++kt) {
         uint32_t pa[4];
         pa[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
         pa[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
@@ -1132,99 +605,47 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
   if (n_win == 0) return HFL_OK;
   HFL_CHECK_ARG(qkv && out && xyzb, "null argument");
   HFL_CHECK_ARG(C == H * AT_HD && H <= 16, "head_dim must be 16, at most 16 heads");
-  HFL_CHECK_ARG(K % 16 == 0 && K + (hat ? 1 : 0) <= AT_KEYS, "window must be a multiple of 16 and (+relay token) fit 80 keys");
+  HFL_CHECK_ARG(K % 16 == 0 && K + (hat ? 1 : 0) <= AT_KEYS, "window must be a multiple of 16 and (+relay token) fit 104 keys");
   HFL_CHECK_ARG(dil >= 1 && (!hat || dil == 1), "dilation is not used with relay tokens");
   HFL_CHECK_ARG(n_win % dil == 0, "window count must be a multiple of the dilation");
-  HFL_CHECK_ARG(bnd >= 0 && (2 * bnd + 3) * 4 < 1024, "RPE bound too large for the packed offsets");
+  HFL_CHECK_ARG(bnd >= 0, "bad RPE bound");
   WinAttnParams p;
   p.qkv = (const __nv_bfloat16*)qkv; p.out = (__nv_bfloat16*)out; p.xyzb = (const short4*)xyzb;
   p.rpe = rpe; p.n_win = (int)n_win; p.H = H; p.C = C; p.K = K; p.dil = dil; p.hat = hat;
   p.bnd = bnd; p.scale = scale;
   const int L = K + (hat ? 1 : 0);
-  const int NT = (L + 7) / 8, NTC = NT * 8, PITCH = NTC + 4;
-  const int sub = 2 * bnd + 3;
-  const char* ver = getenv("HFL_ATTN_V");                  // "1": one head per warp, "2": two heads per warp
-  const bool two = (H % 2 == 0) && !(ver && ver[0] == '1');
-  const Win3Smem lay3 = win3_layout(H, K, hat, bnd);
-  if (H % 8 == 0 && lay3.total <= 227 * 1024 && !(ver && (ver[0] == '1' || ver[0] == '2'))) {
-    // v3: pair bias summed once per 8 heads (see k_window_attn3)
-    // one CTA per SM only (tables > half of the shared memory): 16 warps per window instead of 8
-    const char* w2 = getenv("HFL_ATTN_WPH");
-    const bool wph2 = w2 ? w2[0] == '2' : (2 * lay3.total + 2048 > 227 * 1024 && K >= 32);
-    // experimental: three windows per SM (compact tables, 80 registers) when they fit
-    const Win3Smem layc = win3_layout(H, K, hat, bnd, true);
-    const char* c3 = getenv("HFL_ATTN_CTAS");
-    const bool cps3 = !wph2 && c3 && c3[0] == '3' && 3 * (layc.total + 1024) <= 227 * 1024;
-    const int smem3 = cps3 ? layc.total : lay3.total;
-    const int per_sm = wph2 ? 1 : (cps3 ? 3 : 2);
-    int grid3 = (int)(n_win < per_sm * kSMs ? n_win : per_sm * kSMs);
+  const int NT = (L + 7) / 8;
+  HFL_CHECK_ARG(H % 8 == 0, "the window attention kernel processes heads in groups of 8");
+  Win3Smem lay3 = win3_layout(H, K, hat, bnd);
+  const bool compact = lay3.total > 227 * 1024;
+  if (compact) lay3 = win3_layout(H, K, hat, bnd, true);
+  HFL_CHECK_ARG(lay3.total <= 227 * 1024, "window attention tables exceed shared memory");
+  // one CTA per SM only (tables > half of the shared memory): 16 warps per window instead of 8
+  static const char* w2 = getenv("HFL_ATTN_WPH");
+  const bool wph2 = compact || (w2 ? w2[0] == '2' : (2 * lay3.total + 2048 > 227 * 1024 && K >= 32));
+  const int smem3 = lay3.total;
+  const int per_sm = wph2 ? 1 : 2, sms = sm_count();
+  const int grid3 = (int)(n_win < (int64_t)per_sm * sms ? n_win : per_sm * sms);
 #define HFL_WA3_CASE(NT_)                                                                         \
   case NT_: {                                                                                     \
-    if (wph2) {                                                                                   \
-      static int smem_set3b = 0;                                                                  \
-      if (smem3 > smem_set3b) {                                                                   \
-        HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
-        smem_set3b = smem3;                                                                       \
-      }                                                                                           \
+    if (compact) {                                                                                \
+      HFL_ENSURE_SMEM(smem3, k_window_attn3<NT_, 2, true>);                                       \
+      HFL_LAUNCH((k_window_attn3<NT_, 2, true><<<grid3, 512, smem3, st>>>(p)));                   \
+    } else if (wph2) {                                                                            \
+      HFL_ENSURE_SMEM(smem3, k_window_attn3<NT_, 2>);                                             \
       HFL_LAUNCH((k_window_attn3<NT_, 2><<<grid3, 512, smem3, st>>>(p)));                         \
-      return HFL_OK;                                                                              \
+    } else {                                                                                      \
+      HFL_ENSURE_SMEM(smem3, k_window_attn3<NT_, 1>);                                             \
+      HFL_LAUNCH((k_window_attn3<NT_, 1><<<grid3, 256, smem3, st>>>(p)));                         \
     }                                                                                             \
-    if (cps3) {                                                                                   \
-      static int smem_set3c = 0;                                                                  \
-      if (smem3 > smem_set3c) {                                                                   \
-        HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
-        smem_set3c = smem3;                                                                       \
-      }                                                                                           \
-      HFL_LAUNCH((k_window_attn3<NT_, 1, 3><<<grid3, 256, smem3, st>>>(p)));                      \
-      return HFL_OK;                                                                              \
-    }                                                                                             \
-    static int smem_set3 = 0;                                                                     \
-    if (smem3 > smem_set3) {                                                                      \
-      HFL_CUDA(cudaFuncSetAttribute(k_window_attn3<NT_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3)); \
-      smem_set3 = smem3;                                                                          \
-    }                                                                                             \
-    HFL_LAUNCH((k_window_attn3<NT_, 1><<<grid3, 256, smem3, st>>>(p)));                           \
     return HFL_OK;                                                                                \
   }
-    switch (NT) {
-      HFL_WA3_CASE(2) HFL_WA3_CASE(3) HFL_WA3_CASE(4) HFL_WA3_CASE(5) HFL_WA3_CASE(6) HFL_WA3_CASE(7)
-      HFL_WA3_CASE(8) HFL_WA3_CASE(9) HFL_WA3_CASE(10)
-      default: return fail(HFL_ERR_UNSUPPORTED, "unsupported window size%s (%lld)", "", (long long)K);
-    }
-#undef HFL_WA3_CASE
-  }
-  const int smem = two ? ((H / 2 * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + NTC * 8 +
-                             H * NTC * 4 + H * 2 * NTC * AT_ROW
-                       : ((H * 3 * sub * 4 + 15) & ~15) + (((K + 1) * PITCH * 4 + 15) & ~15) + 2 * NTC * 8 +
-                             H * NTC * 4 + H * 4 * NTC * AT_ROW;
-  HFL_CHECK_ARG(smem <= 227 * 1024, "window attention tables exceed shared memory");
-  int grid = (int)(n_win < 2 * kSMs ? n_win : 2 * kSMs);
-#define HFL_WA_CASE(NT_)                                                                          \
-  case NT_: {                                                                                     \
-    if (two) {                                                                                    \
-      static int smem_set2 = 0;                                                                   \
-      if (smem > smem_set2) {                                                                     \
-        HFL_CUDA(cudaFuncSetAttribute(k_window_attn2<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        smem_set2 = smem;                                                                         \
-      }                                                                                           \
-      HFL_LAUNCH((k_window_attn2<NT_><<<grid, H * 16, smem, st>>>(p)));                           \
-      break;                                                                                      \
-    }                                                                                             \
-    static int smem_set = 0;                                                                      \
-    if (smem > smem_set) {                                                                        \
-      HFL_CUDA(cudaFuncSetAttribute(k_window_attn<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      smem_set = smem;                                                                            \
-    }                                                                                             \
-    HFL_LAUNCH((k_window_attn<NT_><<<grid, H * 32, smem, st>>>(p)));                              \
-    break;                                                                                        \
-  }
   switch (NT) {
-    HFL_WA_CASE(2) HFL_WA_CASE(3) HFL_WA_CASE(4) HFL_WA_CASE(5) HFL_WA_CASE(6) HFL_WA_CASE(7)
-    HFL_WA_CASE(8) HFL_WA_CASE(9) HFL_WA_CASE(10)
+    HFL_WA3_CASE(2) HFL_WA3_CASE(3) HFL_WA3_CASE(4) HFL_WA3_CASE(5) HFL_WA3_CASE(6) HFL_WA3_CASE(7)
+    HFL_WA3_CASE(8) HFL_WA3_CASE(9) HFL_WA3_CASE(10) HFL_WA3_CASE(11) HFL_WA3_CASE(12) HFL_WA3_CASE(13)
     default: return fail(HFL_ERR_UNSUPPORTED, "unsupported window size%s (%lld)", "", (long long)K);
   }
-#undef HFL_WA_CASE
-  return HFL_OK;
+#undef HFL_WA3_CASE
 }
 
 int hfl_varlen_attn(const void* qkv, void* out, const int32_t* cu_seqlens, const int32_t* ids,

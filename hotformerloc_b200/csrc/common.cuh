@@ -39,6 +39,20 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
     HFL_CUDA(cudaPeekAtLastError());                                          \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember the largest size requested per
+// (call site, device) -- no process-wide flag that a second GPU or a racing first call could trip over
+// (worst case two threads both set the attribute, which is idempotent).  __VA_ARGS__ = the kernel.
+#define HFL_ENSURE_SMEM(bytes, ...)                                                               \
+  do {                                                                                            \
+    static std::atomic<int> set__[64];                                                            \
+    int dev__ = 0;                                                                                \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ < 0 || dev__ >= 64) dev__ = 0;              \
+    if (set__[dev__].load(std::memory_order_relaxed) < (int)(bytes)) {                            \
+      HFL_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      set__[dev__].store((int)(bytes), std::memory_order_relaxed);                                \
+    }                                                                                             \
+  } while (0)
+
 constexpr int kSMs = 148;      // B200; grid caps of the small row kernels (any multiple works)
 
 // SM count of the current device (persistent tcgen05 kernels launch one CTA per SM); cached per device.

@@ -744,11 +744,7 @@ int hfl_attn_pool(const float* logits, const float* x, const void* xb, const int
   HFL_CHECK_ARG(C == 256, "C must be 256");
   PoolParams p{logits, x, (const __nv_bfloat16*)xb, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale};
   HFL_LAUNCH((k_pool_stats<<<dim3(B, (kq + 7) / 8), 256, 0, st>>>(p)));
-  static bool attr = false;
-  if (!attr) {
-    HFL_CUDA(cudaFuncSetAttribute(k_pool_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, PM_SMEM));
-    attr = true;
-  }
+  HFL_ENSURE_SMEM(PM_SMEM, k_pool_mma);
   HFL_LAUNCH((k_pool_mma<<<dim3(B, (kq + PM_Q - 1) / PM_Q), 256, PM_SMEM, st>>>(p)));
   return HFL_OK;
 }
@@ -761,11 +757,7 @@ int hfl_mixer_tail(const float* x, const float* wc, const float* bc, const float
   HFL_CHECK_ARG(C == 256 || C == 128, "C must equal the CTA size (128/256)");
   TailParams p{x, wc, bc, wr, br, out, kin, kout, C, od, normalize};
   const int smem = (kout * C + kout * od) * 4;
-  static int smem_set = 48 * 1024;
-  if (smem > smem_set) {
-    HFL_CUDA(cudaFuncSetAttribute(k_mixer_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
+  if (smem > 48 * 1024) HFL_ENSURE_SMEM(smem, k_mixer_tail);
   HFL_LAUNCH((k_mixer_tail<<<B, C, smem, st>>>(p)));
   return HFL_OK;
 }

@@ -119,19 +119,35 @@ def shard_batches(n_items: int, bs: int, rank: int, world: int):
     return [(t, t * bs, min((t + 1) * bs, n_items)) for t in range(n_batches) if t % world == rank]
 
 
-def gather_rows(local: torch.Tensor, spans, n_items: int, rank: int, world: int) -> torch.Tensor:
-    """All-gather rank-local descriptor rows into the (n_items, D) matrix in dataset order.
-    `spans` = this rank's [(t, begin, end)] in the order `local` was filled."""
+def gather_rows(local: torch.Tensor, spans, n_items: int, rank: int, world: int, bs: int = 0) -> torch.Tensor:
+    """All-gather the rank-local descriptor rows into the (n_items, D) matrix in dataset order.
+    `spans` = this rank's [(t, begin, end)] in the order `local` was filled.  One
+    ``all_gather_into_tensor`` of equally sized (zero-padded to the largest shard) blocks: every rank
+    can recompute every other rank's spans from (n_items, bs), so no size exchange is needed
+    (payload ~ n_items * 1 KB: latency bound)."""
     D = local.shape[1]
-    out = torch.zeros((n_items, D), dtype=local.dtype, device=local.device)
-    o = 0
-    for _, b, e in spans:
-        out[b:e] = local[o:o + (e - b)]
-        o += e - b
-    if world > 1:
-        # every row is produced by exactly one rank and zero elsewhere: a sum is a gather
-        # that needs no ragged bookkeeping (payload ~ n_items * 1 KB: latency bound)
-        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    if world == 1:
+        out = torch.empty((n_items, D), dtype=local.dtype, device=local.device)
+        o = 0
+        for _, b, e in spans:
+            out[b:e] = local[o:o + (e - b)]
+            o += e - b
+        return out
+    assert bs > 0, 'the batch size is needed to recompute the other ranks\' shards'
+    all_spans = [shard_batches(n_items, bs, r, world) for r in range(world)]
+    rows = [sum(e - b for _, b, e in sp) for sp in all_spans]
+    assert rows[rank] == local.shape[0]
+    cap = max(max(rows), 1)
+    send = torch.zeros((cap, D), dtype=local.dtype, device=local.device)
+    send[:local.shape[0]] = local
+    recv = torch.empty((world, cap, D), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv.view(world * cap, D), send)
+    out = torch.empty((n_items, D), dtype=local.dtype, device=local.device)
+    for r, sp in enumerate(all_spans):
+        o = 0
+        for _, b, e in sp:
+            out[b:e] = recv[r, o:o + (e - b)]
+            o += e - b
     return out
 
 
@@ -152,6 +168,11 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
         if params.load_octree and params.model_params.coordinates == 'cylindrical' else None
     model.eval()
     keys = list(data_set)
+    if len(keys) == 0:
+        # the reference never allocates `embeddings` for an empty set and returns None
+        # (eval/pnv_evaluate.py:151, 187); evaluate_dataset() skips such pairs.  Every rank sees the
+        # same empty set, so no collective is skipped one-sidedly.
+        return None
     rank, world = _dist_info()
     spans = shard_batches(len(keys), params.val_batch_size, rank, world)
     chunks = []
@@ -190,7 +211,7 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
             torch.set_num_threads(intra)
     dim = params.model_params.output_dim
     local = torch.cat(chunks) if chunks else torch.zeros((0, dim), device=device)
-    return gather_rows(local, spans, len(keys), rank, world).cpu().numpy()
+    return gather_rows(local, spans, len(keys), rank, world, params.val_batch_size).cpu().numpy()
 
 
 def knn_search(database_output: np.ndarray, queries_output: np.ndarray, k: int = NUM_NEIGHBORS):

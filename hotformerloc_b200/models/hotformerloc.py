@@ -202,6 +202,30 @@ class HOTFormer(nn.Module):
             if isinstance(m, nn.Linear):
                 _trunc(m.weight)
                 nn.init.zeros_(m.bias)
+        self._own_engine = None
+
+    def forward(self, data, octree: Octree, depth: int):
+        """Reference signature (hotformerloc_backbone.py:845-849):
+        ``(local_feat_dict {depth: (n_d, C)}, relay_token_dict {depth: (N_win_d, C)}, octree)``.
+        ``data`` must be ``InputFeature('P', nempty=True)(octree)`` -- the leaf point means the first
+        kernel reads straight from the octree (only input_features='P' is on the hot path): it is
+        checked for shape and otherwise not re-read."""
+        if not isinstance(octree, Octree):
+            raise TypeError('octree must be a hotformerloc_b200.octree.Octree')
+        assert depth == octree.depth, 'the backbone starts at the leaf depth of the octree'
+        if data is not None:
+            assert tuple(data.shape) == (octree.n(octree.depth), 3), \
+                "data must be the (n_leaf, 3) 'P' input feature of this octree"
+        if self._own_engine is None:
+            self._own_engine = _Engine(self)
+        return self._outputs(self._own_engine.backbone(octree), octree)
+
+    @staticmethod
+    def _outputs(ctx, octree):
+        K = ctx['K']
+        local = {d: ctx['Xl'][j][ctx['hat_rows'][j].long()] for j, d in enumerate(ctx['depths'])}
+        relay = {d: ctx['Xl'][j][::K + 1] for j, d in enumerate(ctx['depths'])}
+        return local, relay, octree
 
 
 class _AdaptivePooling(nn.Module):
@@ -307,10 +331,22 @@ def _conv_w(conv: _OctConv):
 
 
 class _Engine:
-    def __init__(self, model: 'HOTFormerLoc'):
-        self.m = model
+    """Issues the kernel schedule for a backbone (``HOTFormer``) and, when given, its pooling head."""
+
+    def __init__(self, backbone: 'HOTFormer', pooling: Optional['PoolingWrapper'] = None,
+                 normalize_embeddings: bool = False):
+        self.bb_module = backbone
+        self.pooling = pooling
+        self.normalize_embeddings = normalize_embeddings
         self.sig = None
         self.w: Dict[str, object] = {}
+
+    def _modules(self):
+        return [self.bb_module] + ([self.pooling] if self.pooling is not None else [])
+
+    def invalidate(self):
+        """Forget the repacked weights (call after writing parameters through ``.data``)."""
+        self.sig = None
 
     def _level_streams(self, dev, L):
         """HFL_LEVEL_STREAMS=1: run the pyramid levels of an H-OSA block on separate streams."""
@@ -322,14 +358,17 @@ class _Engine:
         return self._streams[:L]
 
     def _signature(self):
-        ps = list(self.m.parameters()) + list(self.m.buffers())
-        return (ps[0].device, sum(p._version for p in ps), len(ps))
+        # (storage pointer, version counter) of every parameter / buffer: any in-place update through
+        # the autograd-visible API, a load_state_dict, a .to() or a re-assignment changes it.  Writes
+        # through ``p.data`` bump neither: call model.refresh_weights() after those.
+        ps = [t for m in self._modules() for t in list(m.parameters()) + list(m.buffers())]
+        return tuple((t.data_ptr(), t._version) for t in ps)
 
     def prepare(self):
         sig = self._signature()
         if sig == self.sig:
             return self.w
-        bb = self.m.backbone.backbone
+        bb = self.bb_module.backbone
         w: Dict[str, object] = {}
 
         def block(b):
@@ -375,8 +414,10 @@ class _Engine:
         else:
             c = hs.relay_tokeniser.cpe
             w['rt_cpe'] = (_bf(c.conv.weights[:, 0, :]), _f(c.norm.weight), _f(c.norm.bias))
-        pool = self.m.pooling.pooling
-        if isinstance(pool, PyramidAttnPoolWrapper):
+        pool = self.pooling.pooling if self.pooling is not None else None
+        if pool is None:
+            pass
+        elif isinstance(pool, PyramidAttnPoolWrapper):
             qs = []
             for ap in pool.attpool:
                 k, C = ap.query.shape
@@ -430,8 +471,16 @@ class _Engine:
 
     @torch.no_grad()
     def forward(self, octree: Octree, return_intermediates: bool = False):
+        ctx = self.backbone(octree, return_intermediates)
+        out = self.head(ctx)
+        return (out, ctx['inter']) if return_intermediates else out
+
+    @torch.no_grad()
+    def backbone(self, octree: Octree, return_intermediates: bool = False):
+        """PatchEmbed -> OctFormer stage -> HOTFormer stage (hotformerloc_backbone.py:702-723).  Returns the
+        per-level buffers in the hat layout (relay token first in every window) and their row tables."""
         w = self.prepare()
-        cfg = self.m.backbone.cfg
+        cfg = self.bb_module.cfg
         octree.finalize()
         dev = octree.device
         B, D, K, dil = octree.batch_size, octree.depth, cfg['patch_size'], cfg['dilation']
@@ -565,8 +614,14 @@ class _Engine:
             else:
                 ops.gather_gemm(orr, bw['proj'][0], bias=bw['proj'][1], res=X, out_v_f32=X,
                                 ln=bw['n2'], out_y_bf16=yr, out_rows=tabs['rt_rows'])
-                ops.mlp_fused(yr, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X,
-                              out_f32=X, out_rows=tabs['rt_rows'])
+                if _fused_mlp(C1):
+                    ops.mlp_fused(yr, bw['fc1'][0], bw['fc1'][1], bw['fc2'][0], bw['fc2'][1], res=X,
+                                  out_f32=X, out_rows=tabs['rt_rows'])
+                else:
+                    hr = E(T, 4 * C1)
+                    ops.gather_gemm(yr, bw['fc1'][0], bias=bw['fc1'][1], act=1, out_v_bf16=hr)
+                    ops.gather_gemm(hr, bw['fc2'][0], bias=bw['fc2'][1], res=X, out_v_f32=X,
+                                    out_rows=tabs['rt_rows'])
             if lvl_streams is None:
                 for j in range(L):
                     self._block(w['hosa'][j][i], Xl[j], Xbl[j], ne[j], tok[j], nl[j], rows[j], nwin[j],
@@ -585,7 +640,17 @@ class _Engine:
             inter['feats'] = [Xl[j][hat_rows[j].long()].clone() for j in range(L)]
             inter['rts'] = [Xl[j][::K + 1].clone() for j in range(L)]
 
-        # ---------------- pooling head ----------------
+        return dict(Xl=Xl, Xbl=Xbl, hat_rows=hat_rows, tabs=tabs, rows=rows, nl=nl, nwin=nwin, depths=depths,
+                    K=K, B=B, C1=C1, L=L, inter=inter, dev=dev)
+
+    @torch.no_grad()
+    def head(self, ctx):
+        """Pooling head (pooling.py:183-233 / :87-103) + F.normalize (hotformerloc.py:55-56)."""
+        w = self.w
+        Xl, Xbl, tabs, rows, K, B, C1, L, dev = (ctx[k] for k in ('Xl', 'Xbl', 'tabs', 'rows', 'K', 'B', 'C1', 'L',
+                                                                  'dev'))
+        bf, f32 = torch.bfloat16, torch.float32
+        E = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=dev)
         if 'queries' in w:
             ktot = sum(k for _, k, _ in w['queries'])
             Tk = E(B, ktot, C1, dt=f32)
@@ -607,7 +672,7 @@ class _Engine:
             kout, od = t['wc'].shape[0], t['wr'].shape[0]
             out = E(B, kout * od, dt=f32)
             ops.mixer_tail(Tk, t['wc'], t['bc'], t['wr'], t['br'], out, B, ktot, kout, C1, od,
-                           self.m.normalize_embeddings)
+                           self.normalize_embeddings)
         else:
             gw = w['gem']
             pooled = E(B, L * C1, dt=f32)
@@ -616,8 +681,8 @@ class _Engine:
                              L * C1, j * C1)
             g, b, mu, var, eps = gw['bn']
             out = E(B, gw['w'].shape[0], dt=f32)
-            ops.gem_head(pooled, gw['w'], g, b, mu, var, eps, self.m.normalize_embeddings, out)
-        return (out, inter) if return_intermediates else out
+            ops.gem_head(pooled, gw['w'], g, b, mu, var, eps, self.normalize_embeddings, out)
+        return out
 
     def _host_tables(self, octree, depths, nl, npad, nwin, R, K, B):
         """Relay-token ownership / sequence tables (models/octree.py:156-184, 229-265;
@@ -680,13 +745,23 @@ class HOTFormerLoc(nn.Module):
         self.normalize_embeddings = normalize_embeddings
         self.input_features = input_features
         self.stats = {}
-        self._engine = _Engine(self)
+        self._engine = _Engine(backbone, pooling, normalize_embeddings)
+
+    def get_input_feature(self, octree):
+        """InputFeature('P', nempty=True) (hotformerloc.py:28-31): leaf point means in [-1, 1]."""
+        D = octree.depth
+        return octree.points[D] * (2.0 ** (1 - D)) - 1.0
+
+    def refresh_weights(self):
+        """Re-read the parameters on the next forward (needed only after writes through ``.data``)."""
+        self._engine.invalidate()
 
     def forward(self, batch):
         octree = batch['octree']
         if not isinstance(octree, Octree):
             raise TypeError("batch['octree'] must be a hotformerloc_b200.octree.Octree "
-                            '(build it with hotformerloc_b200.octree.build_batch)')
+                            '(build it with hotformerloc_b200.octree.build_batch or merge_octrees)')
+        self._engine.normalize_embeddings = self.normalize_embeddings
         x = self._engine.forward(octree)
         assert x.dim() == 2 and x.shape[1] == self.pooling.output_dim
         return {'global': x}

@@ -30,6 +30,9 @@ def model_factory(model_params: ModelParams):
         ADaPE_mode=mp.ADaPE_mode, grad_checkpoint=mp.grad_checkpoint,
         downsample_input_embeddings=mp.downsample_input_embeddings, disable_RPE=mp.disable_RPE,
         conv_norm=mp.conv_norm, layer_scale=mp.layer_scale, qkv_init=mp.qkv_init, xcpe=mp.xcpe)
+    if mp.pooling == 'PyramidAttnPoolMixer' and mp.channels[-1] != 256:
+        raise NotImplementedError('pooling=PyramidAttnPoolMixer needs 256 channels in the HOTFormer stage '
+                                  '(hfl_attn_pool); no shipped cfg uses another width')
     pooling = PoolingWrapper(
         pool_method=mp.pooling, in_dim=mp.feature_size, output_dim=mp.output_dim,
         num_pyramid_levels=mp.num_pyramid_levels, channels=mp.channels[mp.num_octf_levels:],

@@ -174,9 +174,11 @@ class PinnedPool:
     def __init__(self, slots: int = 4):
         self.slots = [None] * slots
         self.i = 0
+        self.gen = [0] * slots            # how often each slot has been handed out
 
     def take(self, nbytes: int) -> torch.Tensor:
         self.i = (self.i + 1) % len(self.slots)
+        self.gen[self.i] += 1
         slot = self.slots[self.i]
         if slot is not None:
             slot[1].synchronize()
@@ -185,6 +187,13 @@ class PinnedPool:
             slot = [torch.empty(cap, dtype=torch.uint8, pin_memory=True), torch.cuda.Event()]
             self.slots[self.i] = slot
         return slot[0][:nbytes]
+
+    def ticket(self):
+        """Identifies the buffer last taken; valid(ticket) tells whether it is still that hand-out."""
+        return (self.i, self.gen[self.i])
+
+    def valid(self, ticket) -> bool:
+        return self.gen[ticket[0]] == ticket[1]
 
     def mark(self):
         """Call after enqueuing the H2D copy that reads the buffer last taken."""

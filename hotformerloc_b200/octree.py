@@ -48,14 +48,15 @@ class Octree:
         self._neighs = {}
         self._ne = {}                # depth -> (n_d,27) int32 non-empty neighbour table
         self._tok = {}
+        self._src = None             # the input clouds, kept so that merge_octrees can rebuild the batch
 
     # ------------------------------------------------------------------ build
     def build_octree(self, point_cloud: Points):
         """ocnn Octree.build_octree for ONE submap (kept for API parity; the
         batched path is :func:`build_batch`).  Returns the leaf index of every
         point (ocnn's return value)."""
-        o = build_batch([point_cloud.points], self.depth, self.full_depth, self.device,
-                        want_point_leaf=True)
+        pts = point_cloud.points if isinstance(point_cloud, Points) else torch.as_tensor(point_cloud)
+        o = build_batch([pts], self.depth, self.full_depth, self.device, want_point_leaf=True)
         self.__dict__.update(o.__dict__)
         return self._point_leaf.long()
 
@@ -65,6 +66,7 @@ class Octree:
             raise N.HflError('the octree is built on the GPU only (no CPU fallback)')
         B, D, F = len(clouds), self.depth, self.full_depth
         self.batch_size = B
+        self._src = ('host', list(clouds))
         sizes = [int(c.shape[0]) for c in clouds]
         if min(sizes) < 1:
             raise ValueError('every submap needs at least one point')
@@ -132,8 +134,10 @@ class Octree:
         self._desc, self._cap, self._n_points = desc, cap, n
         N.check(L.hfl_octree_build(N.ptr(pts), N.ptr(offs), C.byref(desc), N.ptr(ws), ws_bytes,
                                    N.stream()))
-        # counts -> host (the only D2H of the build; shapes of every later tensor)
+        # counts -> host (the only D2H of the build; shapes of every later tensor).  The pinned slot is
+        # shared and rotates: finalize() re-reads from the device if it was handed out again meanwhile.
         self._counts_host = N.pinned_d2h.take(4 * (D + 1) * (B + 2)).view(torch.int32).view(D + 1, B + 2)
+        self._counts_slot = N.pinned_d2h.ticket()
         self._counts_host.copy_(self._counts_dev.view(D + 1, B + 2), non_blocking=True)
         N.pinned_d2h.mark()
         self._ready = torch.cuda.Event()
@@ -174,7 +178,10 @@ class Octree:
             return self
         self._ready.synchronize()
         B = self.batch_size
-        c = self._counts_host.to(torch.int64)        # copies out of the pinned staging slot
+        if N.pinned_d2h.valid(self._counts_slot):
+            c = self._counts_host.to(torch.int64)    # copies out of the pinned staging slot
+        else:                                        # the slot served a later build: read the device copy
+            c = self._counts_dev.view(self.depth + 1, B + 2).cpu().to(torch.int64)
         self.batch_nnum_nempty = c[:, :B].clone()
         self.nnum_nempty = c[:, B].clone()
         self.nnum = c[:, B + 1].clone()
@@ -319,15 +326,42 @@ def build_batch_device(points: torch.Tensor, offsets: torch.Tensor, depth: int,
     """Same, for points already resident in HBM: (P,3) fp32 + (B+1,) int32 offsets."""
     B = offsets.numel() - 1
     o = Octree(depth, full_depth, B, points.device)
-    o._build_device(points.contiguous(), offsets.contiguous().to(torch.int32),
-                    int(points.shape[0]), False, neigh)
+    points, offsets = points.contiguous(), offsets.contiguous().to(torch.int32)
+    o._src = ('device', points, offsets)
+    o._build_device(points, offsets, int(points.shape[0]), False, neigh)
     return o
 
 
 def merge_octrees(octrees: Sequence[Octree]) -> Octree:
-    """ocnn.octree.merge_octrees (eval/pnv_evaluate.py:123).  Octrees produced by
-    :func:`build_batch` are already merged; merging single-submap octrees
-    re-builds the batch from their retained input clouds."""
+    """ocnn.octree.merge_octrees (eval/pnv_evaluate.py:123): one batch octree from per-submap (or already
+    batched) octrees, submap order = list order.  The merged structure is produced by ONE batched device
+    build over the retained input clouds -- identical, node for node, to concatenating the per-submap
+    octrees with submap ids in the key bits >= 48 and children offset by the running non-empty counts
+    (pinned by the reference's batch_45 fixture), without the O(depth x B) host loop."""
+    octrees = list(octrees)
+    if not octrees:
+        raise ValueError('merge_octrees needs at least one octree')
     if len(octrees) == 1:
         return octrees[0]
-    raise N.HflError('build the batch with hotformerloc_b200.octree.build_batch(clouds, ...)')
+    first = octrees[0]
+    for o in octrees:
+        if not isinstance(o, Octree) or o._src is None:
+            raise N.HflError('merge_octrees: every octree must have been built by Octree.build_octree / build_batch')
+        if (o.depth, o.full_depth) != (first.depth, first.full_depth):
+            raise ValueError('merge_octrees: depth / full_depth differ')
+    if all(o._src[0] == 'host' for o in octrees):
+        clouds = [c for o in octrees for c in o._src[1]]
+        return build_batch(clouds, first.depth, first.full_depth, first.device)
+    pts, offs, base = [], [torch.zeros(1, dtype=torch.int32, device=first.device)], 0
+    for o in octrees:
+        if o._src[0] == 'host':
+            for c in o._src[1]:
+                t = torch.as_tensor(c, dtype=torch.float32).to(first.device)
+                pts.append(t)
+                base += t.shape[0]
+                offs.append(torch.tensor([base], dtype=torch.int32, device=first.device))
+        else:
+            pts.append(o._src[1])
+            offs.append(o._src[2][1:] + base)
+            base += int(o._src[1].shape[0])
+    return build_batch_device(torch.cat(pts), torch.cat(offs), first.depth, first.full_depth)

@@ -8,7 +8,8 @@
  *   - the caller owns every buffer, including workspaces (query the size with
  *     the matching *_workspace_bytes); kernels never allocate or free;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
- *     re-entrant, and keeps no mutable global state;
+ *     and re-entrant; the only process state is idempotent bookkeeping (a launch counter, the
+ *     per-device "dynamic shared memory limit already raised" marks, environment toggles read once);
  *   - every call returns 0 on success or a negative hfl_status; nothing throws
  *     or aborts across the ABI.  hfl_last_error_string() is thread-local.
  *

@@ -183,7 +183,7 @@ n, bs = 1037, 128
 spans = shard_batches(n, bs, rank, world)
 assert [t for t, _, _ in spans] == list(range(rank, (n + bs - 1) // bs, world))
 local = torch.cat([torch.arange(b, e, dtype=torch.float32)[:, None].repeat(1, 4) for _, b, e in spans])
-full = gather_rows(local, spans, n, rank, world)
+full = gather_rows(local, spans, n, rank, world, bs)
 assert torch.equal(full, torch.arange(n, dtype=torch.float32)[:, None].repeat(1, 4)), rank
 dist.destroy_process_group()
 print('ok', rank)
@@ -317,7 +317,7 @@ def test_prefetching_loader_keeps_order_and_batch_composition(tmp_path, monkeypa
 
 
 def test_get_latent_vectors_edge_cases(tmp_path, monkeypatch):
-    """Empty run, a run smaller than one batch, and the reference's --debug short cut
+    """Empty run (-> None, eval/pnv_evaluate.py:151,187), a run smaller than one batch, and the reference's --debug short cut
     (eval/pnv_evaluate.py:131-133: random vectors of the right shape, no model call)."""
     from types import SimpleNamespace
     from hotformerloc_b200.eval import pnv_evaluate as E
@@ -330,8 +330,8 @@ def test_get_latent_vectors_edge_cases(tmp_path, monkeypatch):
                                       val_batch_size=8, dataset_folder=str(tmp_path),
                                       model_params=SimpleNamespace(coordinates='cartesian', output_dim=4), **kw)
     model = SimpleNamespace(eval=lambda: None)
-    out = E.get_latent_vectors(model, {}, 'cpu', mk())
-    assert out.shape == (0, 4) and calls == []
+    # an empty run: None, like the reference (its `embeddings` is never allocated); evaluate_dataset skips it
+    assert E.get_latent_vectors(model, {}, 'cpu', mk()) is None and calls == []
     (tmp_path / 'a.bin').write_bytes(np.zeros((5, 3)).tobytes())
     out = E.get_latent_vectors(model, {7: {'query': 'a.bin'}}, 'cpu', mk())
     assert out.shape == (1, 4) and calls == [1]

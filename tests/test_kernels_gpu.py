@@ -189,7 +189,8 @@ def _ref_window_attn(qkv, tok, rpe, K, dil, hat, H, bnd):
 
 
 @pytest.mark.parametrize('K,dil,hat,H', [(48, 1, False, 8), (48, 4, False, 8), (48, 1, True, 16),
-                                         (64, 1, True, 16), (64, 4, False, 8), (32, 1, True, 8)])
+                                         (64, 1, True, 16), (64, 4, False, 8), (32, 1, True, 8),
+                                         (96, 1, True, 16), (96, 4, False, 8), (96, 1, False, 16)])
 def test_window_attention(K, dil, hat, H):
     torch.manual_seed(3)
     C = 16 * H

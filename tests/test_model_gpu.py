@@ -114,3 +114,40 @@ def test_full_size_batch_properties(tmp_path):
     cos = torch.nn.functional.cosine_similarity(solo, y1[:1]).item()
     print(f'submap 0 alone vs in the 256-batch: cos {cos:.7f}, max-abs {(solo - y1[:1]).abs().max().item():.2e}')
     assert cos >= 0.9999
+
+
+def test_backbone_forward_signature_and_weight_refresh(tmp_path):
+    """HOTFormer.forward(data, octree, depth) -> (local_feat_dict, relay_token_dict, octree)
+    (hotformerloc_backbone.py:845-849) against the oracle's per-level features; the reference call flow
+    HOTFormerLoc.get_input_feature -> backbone -> pooling; weights written through .data are picked up
+    after refresh_weights()."""
+    name = 'oxford_b4_stress'
+    cfg, depth, spec, seed, mode = CASES[name]
+    model, octree, clouds, sd, paths = _run(name, tmp_path)
+    data = model.get_input_feature(octree)
+    assert tuple(data.shape) == (octree.n(depth), 3) and float(data.abs().max()) <= 1.0
+    local, relay, oct2 = model.backbone(data=data, octree=octree, depth=octree.depth)
+    assert oct2 is octree
+    hp = M.HParams.from_cfg(paths['model_config'])
+    g, ref = M.forward(sd, R.build_batch(clouds, depth), hp, return_intermediates=True)
+    d0 = depth - 2
+    assert sorted(local) == sorted(relay) == [d0 - 3, d0 - 2, d0 - 1]
+    for j, d in enumerate((d0 - 1, d0 - 2, d0 - 3)):
+        a, b = local[d].float().cpu(), ref['feats'][j].float()
+        assert a.shape == b.shape
+        assert float((a - b).norm() / b.norm()) < 5e-2, d
+        nreal = -(-b.shape[0] // hp.patch_size)
+        ra, rb = relay[d][:nreal].float().cpu(), ref['rts'][j][:nreal].float()
+        assert float((ra - rb).norm() / rb.norm()) < 5e-2, d
+    # same descriptors as the one-call path
+    y = model({'octree': octree})['global'].float()
+    assert cosine(y.cpu().numpy(), g.numpy()).min() >= 0.999
+    # parameters overwritten through .data: stale until refresh_weights()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.data.mul_(1.0)
+        model.pooling.pooling.descriptor_extractor.row_proj.weight.data.mul_(-1.0)
+        model.pooling.pooling.descriptor_extractor.row_proj.bias.data.mul_(-1.0)
+    model.refresh_weights()
+    y2 = model({'octree': octree})['global'].float()
+    assert torch.allclose(y2, -y, atol=1e-6)

@@ -122,3 +122,38 @@ def test_errors_are_reported_not_thrown_across_abi():
         build_batch([np.zeros((0, 3), np.float32)], 7)
     with pytest.raises(AssertionError):
         build_batch([np.zeros((4, 3), np.float32)], 3, full_depth=3)
+
+
+def test_reference_call_flow_build_then_merge():
+    """The reference's eval loop builds one octree per submap and merges them
+    (eval/pnv_evaluate.py:173-175, :122-126): Octree(depth, full_depth=2).build_octree(Points(x)) ...
+    merge_octrees(list).  The merged octree must equal the batched build bit for bit, also when
+    more octrees are built before an earlier one is finalised than the pinned read-back pool has slots."""
+    from hotformerloc_b200.octree import Octree, Points, build_batch, merge_octrees
+    g = torch.Generator().manual_seed(31)
+    clouds = [M.lidar_cloud(n, g) for n in (4096, 300, 4096, 1, 2500, 4096, 77, 4096, 1500, 4096, 900, 64)]
+    singles = []
+    for c in clouds:
+        o = Octree(7, full_depth=2)
+        idx = o.build_octree(Points(torch.from_numpy(c)))
+        assert idx.shape == (len(c),)
+        singles.append(o)
+    # 12 builds in flight > 8 pinned slots: every per-submap octree must still report ITS OWN counts
+    r1 = [R.build_batch([c], 7) for c in clouds]
+    for o, r in zip(singles, r1):
+        assert np.array_equal(o.finalize().nnum_nempty.numpy(), r.nnum_nempty)
+        assert np.array_equal(o.nnum.numpy(), r.nnum)
+    merged = merge_octrees(singles)
+    ref = R.build_batch(clouds, 7)
+    direct = build_batch(clouds, 7, 2, 'cuda')
+    assert merged.batch_size == len(clouds)
+    for d in range(8):
+        assert np.array_equal(merged.keys[d].cpu().numpy(), ref.keys[d]), d
+        assert np.array_equal(merged.children[d].cpu().numpy(), ref.children[d]), d
+        assert torch.equal(merged.keys[d], direct.keys[d])
+    assert np.array_equal(merged.batch_nnum_nempty.numpy(), ref.batch_nnum_nempty)
+    # merging already-batched octrees keeps the submap order
+    two = merge_octrees([build_batch(clouds[:5], 7, 2, 'cuda'), build_batch(clouds[5:], 7, 2, 'cuda')])
+    for d in range(8):
+        assert torch.equal(two.keys[d], direct.keys[d])
+        assert torch.equal(two.children[d], direct.children[d])
