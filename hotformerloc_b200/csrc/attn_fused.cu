@@ -10,23 +10,30 @@
 // group of four heads,
 //   1. QKV chunk  D[128 x 192] = y_tile . Wg^T          tcgen05.mma M=128 N=192 (K = C), y tile by TMA,
 //                                                        weights streamed from L2 through a TMA ring
-//   2. drain      TMEM -> +bias -> bf16 -> shared memory as UMMA operands: Q, K (K-major, 128B swizzle)
-//                 and V^T (dims x keys, K-major)
-//   3. per head   S = Q_h K_h^T                          ONE tcgen05.mma (M=128, N=128, K=16) into TMEM
-//                 softmax: thread == query row; the row's scores come out of tensor memory
-//                 (tcgen05.ld), bias = three fp32 table look-ups per pair at offsets cached in registers
-//                 for the whole tile (block-invariant pair codes), P (bf16) goes back INTO tensor memory
-//                 over S (tcgen05.st)
-//                 O_h = P V_h                            tcgen05.mma with the A operand in tensor memory
-//                                                        (M=128, N=16, K=128: own window's keys, zeros for
-//                                                        the other window slot)
+//   2. drain      TMEM -> +bias -> bf16 -> shared memory as UMMA operands.  Per window: a BLOCK-DIAGONAL Q tile
+//                 (row (parity, query) holds the 16 dims of head 2 hp + parity at K columns hp * 32 + parity * 16,
+//                 zeros in the other parity's columns), a K tile (row key, same columns) and V^T tiles
+//                 (row parity * 16 + dim, columns = keys) per head pair hp
+//   3. per unit = (window, head pair):
+//                 S[(parity, query)][key] = Q_{2 hp + parity}[query] . K_{2 hp + parity}[key]
+//                                                        TWO tcgen05.mma (M=128, N=64, K=32) into a 64-column
+//                                                        accumulator: every entry is a needed score
+//                 softmax: thread == (query, head) row with ALL its keys (tcgen05.ld; row max / row sum are
+//                 thread-local); bias = three fp16-pair table look-ups per (query, key) at offsets cached in
+//                 registers for the whole tile, one look-up serving both units of the group; P (bf16) goes
+//                 back INTO tensor memory over the scores (tcgen05.st, columns 0-31)
+//                 O[(parity, query)][parity' * 16 + dim] = P . V_{2 hp + parity'}
+//                                                        tcgen05.mma, A operand in tensor memory (M=128, N=32,
+//                                                        K = keys rounded up to 16) into columns 32-63 of the
+//                                                        unit's buffer; the row keeps the half of its own head
 //   4. O drain    TMEM -> 1/rowsum -> bf16 -> global (32 B per row and head)
-// Warp roles (576 threads, 1 CTA / SM, persistent over tiles):
-//   0-15 softmax / drain: lane quadrant = warp % 4 (thread == row), warp / 4 = which quarter of the row's
-//        keys the thread evaluates (row maximum bound and row sum are combined through shared memory);
-//        they also drain the QKV chunk (three 16-column units each) and one head's output each
-//   16   tcgen05.mma issue + TMEM alloc          17  TMA producer (lanes 0-1 weights, lane 2 y tiles)
-// Tensor memory (512 columns): QKV chunk 0-191 | S/P buffer 0: 192-319 | S/P buffer 1: 320-447 | O: 448-511.
+// Warp roles (320 threads, 168 registers, 1 CTA / SM, persistent over tiles):
+//   0-7  softmax / drain: team = warp / 4 = window slot of the tile, lane quadrant = warp % 4; per head group
+//        the team drains half of the QKV chunk and runs its two units one after the other (the PV product
+//        of the first overlaps the softmax of the second); the two teams are not synchronised with each other
+//        inside a group
+//   8    tcgen05.mma issue + TMEM alloc          9   TMA producer (lanes 0-1 weights, lane 2 y tiles)
+// Tensor memory (512 columns): QKV chunk 0-191 | four unit buffers of 64 columns at 192 + 64 (2 window + hp).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -36,7 +43,7 @@
 
 namespace hfl {
 
-constexpr int QA_THREADS = 576;           // 16 softmax / drain warps + MMA issuer + TMA producer
+constexpr int QA_THREADS = 320;           // 8 softmax / drain warps + MMA issuer + TMA producer (168 registers)
 constexpr int QA_SLOT_ROWS = 64;           // rows per window slot (2 slots per 128-row tile)
 constexpr int QA_GN = 192;                 // QKV columns per head group: q | k | v of 4 heads
 constexpr int QA_W_SLOT = QA_GN * 128;     // one K block of a group's weights: 192 rows x 64 bf16
@@ -48,16 +55,14 @@ struct QaSmem {
   static constexpr int KB = C / 64;
   static constexpr int Y_BYTES = KB * 16384;
   static constexpr int OFF_W = Y_BYTES;
-  static constexpr int OFF_Q = OFF_W + QA_RING * QA_W_SLOT;
-  static constexpr int OFF_K = OFF_Q + 16384;
-  static constexpr int OFF_V = OFF_K + 16384;          // V^T: [4 heads][2 key blocks][16 dims x 128 B]
-  static constexpr int OFF_TOK = OFF_V + 16384;        // [128] int4: 4x, 4y, 4z, submap
-  static constexpr int OFF_MX = OFF_TOK + 2048;        // [2][4 parts][128 rows] fp32 row-max exchange
-  static constexpr int OFF_L = OFF_MX + 4096;          // [4 heads][4 parts][128 rows] fp32 partial row sums
-  static constexpr int OFF_BMAX = OFF_L + 8192;        // [16] fp32 largest bias of a head
-  static constexpr int OFF_BIAS = OFF_BMAX + 64;       // [3C] fp32, group-major like the weights
+  static constexpr int OFF_A = OFF_W + QA_RING * QA_W_SLOT;   // [2 windows] 128 rows x 128 B: block-diagonal Q
+  static constexpr int OFF_K = OFF_A + 2 * 16384;             // [2 windows] 64 keys x 128 B
+  static constexpr int OFF_V = OFF_K + 2 * 8192;              // [2 windows][2 head pairs] V^T: 32 x 128 B (64 keys)
+  static constexpr int OFF_TOK = OFF_V + 4 * 4096;            // [128] int4: 4x, 4y, 4z, submap
+  static constexpr int OFF_BMAX = OFF_TOK + 2048;             // [16] fp32 largest bias of a head
+  static constexpr int OFF_BIAS = OFF_BMAX + 64;              // [3C] fp32, group-major like the weights
   static constexpr int OFF_BAR = OFF_BIAS + 3 * C * 4;
-  static constexpr int OFF_TAB = OFF_BAR + 256;        // RPE tables [3][H / 2][SUBP] fp16 pairs (even, odd head) x log2 e
+  static constexpr int OFF_TAB = OFF_BAR + 256;               // RPE tables [3][H / 4][2][SUBP] fp16 pairs x log2 e
 };
 
 struct QaParams {
@@ -102,48 +107,39 @@ __device__ __forceinline__ float qa_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// store N consecutive tensor-memory columns from registers (N compile-time: powers of two, greedily)
-template <int N>
-__device__ __forceinline__ void qa_st_cols(uint32_t a, const uint32_t* v) {
-  if constexpr (N >= 16) { uint32_t t[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = v[i];
-    ptx::tmem_st16(a, t); qa_st_cols<N - 16>(a + 16, v + 16); }
-  else if constexpr (N >= 8) { ptx::tmem_st8(a, v); qa_st_cols<N - 8>(a + 8, v + 8); }
-  else if constexpr (N >= 4) { ptx::tmem_st4(a, v); qa_st_cols<N - 4>(a + 4, v + 4); }
-  else if constexpr (N >= 2) { ptx::tmem_st2(a, v); qa_st_cols<N - 2>(a + 2, v + 2); }
-  else if constexpr (N >= 1) { ptx::tmem_st1(a, v); }
-}
-// NV value columns followed by zeros up to NTOT columns
-template <int NV, int NTOT>
-__device__ __forceinline__ void qa_st_cols_tail(uint32_t a, const uint32_t* v) {
-  uint32_t t[NTOT];
-#pragma unroll
-  for (int i = 0; i < NTOT; ++i) t[i] = i < NV ? v[i] : 0u;
-  qa_st_cols<NTOT>(a, t);
-}
 __device__ __forceinline__ uint32_t qa_pack(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// load / store N consecutive tensor-memory columns (N compile-time: powers of two, greedily)
+template <int N>
+__device__ __forceinline__ void qa_ld_cols(uint32_t a, uint32_t* v) {
+  if constexpr (N >= 16) { uint32_t t[16]; ptx::tmem_ld16(a, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = t[i];
+    qa_ld_cols<N - 16>(a + 16, v + 16); }
+  else if constexpr (N >= 8) { ptx::tmem_ld8(a, v); qa_ld_cols<N - 8>(a + 8, v + 8); }
+  else if constexpr (N >= 4) { ptx::tmem_ld4(a, v); qa_ld_cols<N - 4>(a + 4, v + 4); }
+  else if constexpr (N >= 2) { ptx::tmem_ld2(a, v); qa_ld_cols<N - 2>(a + 2, v + 2); }
+  else if constexpr (N >= 1) { ptx::tmem_ld1(a, v); }
+}
 
-// NKEY: keys of a window (K + relay token; <= 64) -- exact, so that the per-row register arrays (pair
-// codes + scores) carry no padding
 #define QA_T0() const long long t0_ = PROF ? clock64() : 0
 #define QA_ACC(slot) do { if (PROF) lacc[slot] += clock64() - t0_; } while (0)
 
+// NKEY: keys of a window (K + relay token; <= 64) -- exact, so that the per-row register array of pair
+// codes carries no padding
 template <int C, int NKEY, bool PROF>
 __global__ void __launch_bounds__(QA_THREADS, 1)
 k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w, const QaParams p) {
   using S = QaSmem<C>;
   constexpr int KB = S::KB, G = C / 64;                  // K blocks of the projection, head groups
+  constexpr int NCH = (NKEY + 15) / 16;                  // 16-key chunks of a row = K steps of the PV product
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = ptx::smem_u32(smem);
   if (base & 1023u) __trap();
-  const uint32_t sY = base, sW = base + S::OFF_W, sQ = base + S::OFF_Q, sK = base + S::OFF_K, sV = base + S::OFF_V;
+  const uint32_t sY = base, sW = base + S::OFF_W, sA = base + S::OFF_A, sK = base + S::OFF_K, sV = base + S::OFF_V;
   int4* s_tok = reinterpret_cast<int4*>(smem + S::OFF_TOK);
-  float* s_mx = reinterpret_cast<float*>(smem + S::OFF_MX);
-  float* s_l = reinterpret_cast<float*>(smem + S::OFF_L);
   float* s_bmax = reinterpret_cast<float*>(smem + S::OFF_BMAX);
   float* s_bias = reinterpret_cast<float*>(smem + S::OFF_BIAS);
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + S::OFF_TAB);
@@ -151,12 +147,12 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
   const uint32_t y_full = bar, y_empty = bar + 8;
   const uint32_t w_full = bar + 16, w_empty = bar + 16 + 8 * QA_RING;      // QA_RING each
   const uint32_t chunk_full = bar + 64, qkv_ready = bar + 72, attn_done = bar + 80;
-  const uint32_t s_full = bar + 88;      // [2]
-  const uint32_t p_ready = bar + 104;    // [2]
-  const uint32_t o_full = bar + 120;     // [4]
-  const uint32_t o_free = bar + 152;     // [4]
-  const uint32_t s_tmem = bar + 184;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 184);
+  const uint32_t s_full = bar + 88;      // [4]  S of a unit is in tensor memory
+  const uint32_t p_ready = bar + 120;    // [4]  P of a unit is in tensor memory
+  const uint32_t o_full = bar + 152;     // [4]  O of a unit is in tensor memory
+  const uint32_t o_free = bar + 184;     // [4]  O of a unit has been read: its buffer may take the next S
+  const uint32_t s_tmem = bar + 216;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 216);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = p.K, hat = p.hat, L = K + hat, H = p.H, dil = p.dil;
@@ -168,17 +164,19 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
   for (int i = 0; i < 16; ++i) lacc[i] = 0;
   const long long t_role = PROF ? clock64() : 0;
 
-  // ---- one-time setup: bias vector, RPE tables (x log2 e; slot num = 0, slot num + 1 of the x axis = -inf) ----
+  // ---- one-time setup: bias vector, RPE tables (x log2 e; slot num = 0, slot num + 1 of the x axis = -inf),
+  //      zeros in the block-diagonal Q tiles (the off-diagonal chunks are never written again) ----
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_bias[i] = p.bias[i];
-  // one 4-byte entry = the biases of an (even, odd) pair of heads as fp16: a look-up serves two heads and
-  // neighbouring offsets share a bank word (half the bank conflicts of an fp32 table)
+  // one 4-byte entry = the fp16 biases of the two heads a softmax thread owns in a head group
+  // (4 grp + par, 4 grp + 2 + par): one look-up per axis serves both units of the group
   for (int i = threadIdx.x; i < 3 * (H / 2) * SUBP; i += blockDim.x) {
-    const int k = i % SUBP, hp = (i / SUBP) % (H / 2), axis = i / (SUBP * (H / 2));
+    const int k = i % SUBP, gp = (i / SUBP) % (H / 2), axis = i / (SUBP * (H / 2));
+    const int h0 = (gp >> 1) * 4 + (gp & 1), h1 = h0 + 2;
     float v0 = 0.f, v1 = 0.f;
     if (k < num) {
       if (p.rpe) {
-        v0 = __ldg(p.rpe + (size_t)(axis * num + k) * H + 2 * hp) * QA_LOG2E;
-        v1 = __ldg(p.rpe + (size_t)(axis * num + k) * H + 2 * hp + 1) * QA_LOG2E;
+        v0 = __ldg(p.rpe + (size_t)(axis * num + k) * H + h0) * QA_LOG2E;
+        v1 = __ldg(p.rpe + (size_t)(axis * num + k) * H + h1) * QA_LOG2E;
       }
     } else if (k == num + 1 && axis == 0) {
       v0 = v1 = -INFINITY;
@@ -186,40 +184,49 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     const __half2 hv = __floats2half2_rn(v0, v1);
     s_tab[i] = *reinterpret_cast<const uint32_t*>(&hv);
   }
+  for (int i = threadIdx.x; i < 2 * 16384 / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem + S::OFF_A)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
     ptx::mbar_init(y_full, 1);
     ptx::mbar_init(y_empty, 1);
     for (int s = 0; s < QA_RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
     ptx::mbar_init(chunk_full, 1);
-    ptx::mbar_init(qkv_ready, 16);
+    ptx::mbar_init(qkv_ready, 8);
     ptx::mbar_init(attn_done, 1);
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(s_full + 8 * b, 1); ptx::mbar_init(p_ready + 8 * b, 16); }
-    for (int h = 0; h < 4; ++h) { ptx::mbar_init(o_full + 8 * h, 1); ptx::mbar_init(o_free + 8 * h, 4); }
+    for (int t = 0; t < 4; ++t) {
+      ptx::mbar_init(s_full + 8 * t, 1);
+      ptx::mbar_init(p_ready + 8 * t, 4);
+      ptx::mbar_init(o_full + 8 * t, 1);
+      ptx::mbar_init(o_free + 8 * t, 4);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 16) { ptx::tmem_alloc(s_tmem, 512); ptx::tmem_relinquish(); }
+  if (warp == 8) { ptx::tmem_alloc(s_tmem, 512); ptx::tmem_relinquish(); }
+  ptx::fence_proxy_async();                              // the zeroed Q tiles are read by the tensor core
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   // largest bias a head can add (sum of the per-axis table maxima): part of the exponent shift
   if (threadIdx.x < H) {
+    const int h = threadIdx.x, gp = (h >> 2) * 2 + (h & 1), hi = (h >> 1) & 1;
     float tot = 0.f;
     for (int axis = 0; axis < 3; ++axis) {
       float m = 0.f;                                       // the zero slot is always reachable
       for (int k = 0; k < num; ++k) {
-        const uint32_t e = s_tab[(axis * (H / 2) + (threadIdx.x >> 1)) * SUBP + k];
+        const uint32_t e = s_tab[(axis * (H / 2) + gp) * SUBP + k];
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&e));
-        m = fmaxf(m, (threadIdx.x & 1) ? f.y : f.x);
+        m = fmaxf(m, hi ? f.y : f.x);
       }
       tot += m;
     }
-    s_bmax[threadIdx.x] = tot;
+    s_bmax[h] = tot;
   }
   __syncthreads();
   const uint32_t tmem_base = *tmem_ptr_s;
-  constexpr uint32_t T_CHUNK = 0, T_S = 192, T_O = 448;
+  // tensor memory: QKV chunk 0-191 | four unit buffers of 64 columns (S, then P in 0-31 and O in 32-63)
+  constexpr uint32_t T_CHUNK = 0, T_U = 192;
 
-  if (warp == 17) {
+  if (warp == 9) {
     // ===================== TMA producer =====================
     if (lane < 2) {
       ptx::prefetch_tmap(&tm_w);
@@ -250,13 +257,13 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 16) {
+  } else if (warp == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_qkv = ptx::umma_idesc_bf16(128, QA_GN);
-      const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128);
-      const uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 16);
-      uint32_t ring = 0, gcount = 0, pcnt[2] = {0, 0};
+      const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64);
+      const uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 32);
+      uint32_t ring = 0, gcount = 0;
       auto issue_qkv = [&](int grp) {
         for (int kb = 0; kb < KB; ++kb, ++ring) {
           const uint32_t s = ring % QA_RING, ph = (ring / QA_RING) & 1;
@@ -272,35 +279,49 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
         ptx::umma_commit(chunk_full);
         if (grp == G - 1) ptx::umma_commit(y_empty);
       };
-      auto issue_s = [&](int hl) {
-        const uint32_t buf = hl & 1;
-        ptx::umma_bf16(tmem_base + T_S + buf * 128, ptx::umma_desc_sw128(sQ) + 2 * hl,
-                       ptx::umma_desc_sw128(sK) + 2 * hl, idesc_s, 0);
-        ptx::umma_commit(s_full + 8 * buf);
-      };
+      bool first_issued = false;                           // chunk 0 of this tile was issued during the previous tile
       for (int it = 0; it < n_my; ++it) {
-        { QA_T0(); ptx::mbar_wait(y_full, it & 1); QA_ACC(1); }
-        ptx::tc_fence_after();
-        issue_qkv(0);
+        if (!first_issued) {
+          { QA_T0(); ptx::mbar_wait(y_full, it & 1); QA_ACC(1); }
+          ptx::tc_fence_after();
+          issue_qkv(0);
+        }
+        first_issued = false;
         for (int grp = 0; grp < G; ++grp, ++gcount) {
           { QA_T0(); ptx::mbar_wait(qkv_ready, gcount & 1); QA_ACC(2); }   // Q / K / V^T of this group are in shared memory
           ptx::tc_fence_after();
-          issue_s(0);
-          issue_s(1);
-          if (grp + 1 < G) issue_qkv(grp + 1);            // the chunk columns were drained before qkv_ready
-          for (int hl = 0; hl < 4; ++hl) {
-            const uint32_t buf = hl & 1;
-            { QA_T0(); ptx::mbar_wait(p_ready + 8 * buf, pcnt[buf] & 1); QA_ACC(3); }
-            ++pcnt[buf];
-            if (gcount > 0) { QA_T0(); ptx::mbar_wait(o_free + 8 * hl, (gcount - 1) & 1); QA_ACC(4); }
-            ptx::tc_fence_after();
+          // unit t = (window ws = t / 2, head pair hp = t % 2): S[(parity, query)][key] for both heads of the
+          // pair in ONE accumulator through the block-diagonal Q tile (K = 32: 16 dims x 2 heads)
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              ptx::umma_bf16_ts(tmem_base + T_O + hl * 16, tmem_base + T_S + buf * 128 + 8 * kk,
-                                ptx::umma_desc_sw128(sV + hl * 4096 + (kk >> 2) * 2048) + 2 * (kk & 3), idesc_pv,
-                                kk != 0);
-            ptx::umma_commit(o_full + 8 * hl);
-            if (hl + 2 < 4) issue_s(hl + 2);
+          for (int t = 0; t < 4; ++t) {
+            const int ws = t >> 1, hp = t & 1;
+            if (gcount > 0) { QA_T0(); ptx::mbar_wait(o_free + 8 * t, (gcount - 1) & 1); QA_ACC(4); }
+            ptx::tc_fence_after();
+            const uint64_t ad = ptx::umma_desc_sw128(sA + ws * 16384) + 4 * hp;
+            const uint64_t bd = ptx::umma_desc_sw128(sK + ws * 8192) + 4 * hp;
+            ptx::umma_bf16(tmem_base + T_U + t * 64, ad, bd, idesc_s, 0);
+            ptx::umma_bf16(tmem_base + T_U + t * 64, ad + 2, bd + 2, idesc_s, 1);
+            ptx::umma_commit(s_full + 8 * t);
+          }
+          // next projection chunk (the chunk columns were drained before qkv_ready); across the tile boundary
+          // only if the next y tile has already landed (never stall the PV issue on it)
+          if (grp + 1 < G) issue_qkv(grp + 1);
+          else if (it + 1 < n_my && ptx::mbar_try_wait(y_full, (it + 1) & 1)) {
+            ptx::tc_fence_after();
+            issue_qkv(0);
+            first_issued = true;
+          }
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            const int t = (tt & 1) * 2 + (tt >> 1);          // the order the teams finish them: 0, 2, 1, 3
+            { QA_T0(); ptx::mbar_wait(p_ready + 8 * t, gcount & 1); QA_ACC(3); }
+            ptx::tc_fence_after();
+            const uint64_t vd = ptx::umma_desc_sw128(sV + t * 4096);
+#pragma unroll
+            for (int kk = 0; kk < NCH; ++kk)
+              ptx::umma_bf16_ts(tmem_base + T_U + t * 64 + 32, tmem_base + T_U + t * 64 + 8 * kk, vd + 2 * kk,
+                                idesc_pv, kk != 0);
+            ptx::umma_commit(o_full + 8 * t);
           }
           ptx::umma_commit(attn_done);
         }
@@ -309,132 +330,116 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     }
     __syncwarp();
   } else {
-    // ===================== softmax / drain warps 0-15 =====================
-    // quad = TMEM lane quadrant (hardware: warp % 4); the four warps of a quadrant split the KEYS of a row:
-    // thread (row r, part) owns keys [part * KP, ...) of every head -- 13 keys instead of 49 per thread
-    // keeps the per-thread state small enough for 16 resident softmax warps (4 per scheduler).
+    // ===================== softmax / drain warps 0-7 =====================
+    // team = warp / 4 owns window slot ws = team of the tile: per head group its two units (head pairs), one
+    // after the other; quad = TMEM lane quadrant (hardware: warp % 4).  In a unit's accumulator lane
+    // r = (head parity r / 64, query slot r % 64): the thread owns one (query, head) row with ALL its keys --
+    // row maximum and row sum are thread-local, nothing is exchanged between threads.
     const int wq = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
-    const int quad = wq & 3, part = wq >> 2;
-    const int r = quad * 32 + lane, ws = r >> 6, sl = r & 63;
-    constexpr int KP = (NKEY / 4) & ~1;                    // keys per part (even: bf16 pairs stay thread-local)
-    constexpr int KMAX = NKEY - 3 * KP;                    // the last part takes the remainder (>= KP)
-    static_assert(KMAX <= 16 && KP >= 2, "key split does not fit the x16 tensor-memory loads");
-    const int k0 = part * KP, nk = part == 3 ? KMAX : KP;
+    const int quad = wq & 3, team = wq >> 2;
+    const int r = quad * 32 + lane;
+    const int par = r >> 6, sl = r & 63;                   // softmax view of the lane
+    const int ws = team;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float sc = p.scale * QA_LOG2E;
     const bool use_rpe = p.rpe != nullptr;
     const uint32_t tab_u = base + S::OFF_TAB;
     const int o_zero = num * 4, o_inf = (num + 1) * 4;
     const int bnd4 = p.bnd * 4;
-    uint32_t gcount = 0, hcount = 0;                       // groups done, heads done
+    uint32_t gcount = 0;
 
-    // output of head `part` of group number gc (group index grp_o within its tile): O / rowsum -> bf16 -> global
-    auto drain_o = [&](uint32_t gc, int grp_o, int64_t row_o, bool valid_o) {
-      const int hl = part, h = grp_o * 4 + hl;
-      { QA_T0(); ptx::mbar_wait(o_full + 8 * hl, gc & 1); QA_ACC(13); }
-      ptx::tc_fence_after();
-      const long long t_od = PROF ? clock64() : 0;
-      uint32_t ro[16];
-      ptx::tmem_ld16(lane_base + T_O + hl * 16, ro);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(o_free + 8 * hl);
-      if (valid_o) {
-        const float* lp = s_l + hl * 512 + r;
-        const float s = 1.0f / fmaxf((lp[0] + lp[128]) + (lp[256] + lp[384]), 1e-37f);
-        uint4 a, b;
-        a.x = qa_pack(__uint_as_float(ro[0]) * s, __uint_as_float(ro[1]) * s);
-        a.y = qa_pack(__uint_as_float(ro[2]) * s, __uint_as_float(ro[3]) * s);
-        a.z = qa_pack(__uint_as_float(ro[4]) * s, __uint_as_float(ro[5]) * s);
-        a.w = qa_pack(__uint_as_float(ro[6]) * s, __uint_as_float(ro[7]) * s);
-        b.x = qa_pack(__uint_as_float(ro[8]) * s, __uint_as_float(ro[9]) * s);
-        b.y = qa_pack(__uint_as_float(ro[10]) * s, __uint_as_float(ro[11]) * s);
-        b.z = qa_pack(__uint_as_float(ro[12]) * s, __uint_as_float(ro[13]) * s);
-        b.w = qa_pack(__uint_as_float(ro[14]) * s, __uint_as_float(ro[15]) * s);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + row_o * C + h * 16);
-        dst[0] = a;
-        dst[1] = b;
-      }
-      if (PROF) lacc[14] += clock64() - t_od;
-    };
     for (int it = 0; it < n_my; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      const int w = tile * 2 + ws;
-      const bool valid = w < p.n_win && sl < L;
-      // layout row of this thread's slot and the token behind it
-      int64_t row, tok;
-      if (hat) { row = (int64_t)w * L + sl; tok = (int64_t)w * K + (sl == 0 ? 0 : sl - 1); }
-      else if (dil > 1) { row = (int64_t)(w / dil) * K * dil + (int64_t)sl * dil + (w % dil); tok = row; }
-      else { row = (int64_t)w * K + sl; tok = row; }
-      if (part == 0) {
-        // coordinates pre-multiplied by 4: clamp(4 dx, +-4 bnd) + 4 bnd is the byte offset into an fp32 table
-        const short4 tk = valid ? __ldg(p.xyzb + tok) : make_short4(0, 0, 0, -2);
+      // token table of the tile: thread r of team 0 loads the token of y-tile row r (window r / 64, slot r % 64)
+      if (team == 0) {
+        const int w0 = tile * 2 + (r >> 6);
+        const bool v0 = w0 < p.n_win && sl < L;
+        int64_t tok0;
+        if (hat) tok0 = (int64_t)w0 * K + (sl == 0 ? 0 : sl - 1);
+        else if (dil > 1) tok0 = (int64_t)(w0 / dil) * K * dil + (int64_t)sl * dil + (w0 % dil);
+        else tok0 = (int64_t)w0 * K + sl;
+        // coordinates pre-multiplied by 4: clamp(4 dx, +-4 bnd) + 4 bnd is the byte offset into a table of 4-byte entries
+        const short4 tk = v0 ? __ldg(p.xyzb + tok0) : make_short4(0, 0, 0, -2);
         s_tok[r] = make_int4(4 * (int)tk.x, 4 * (int)tk.y, 4 * (int)tk.z, (int)tk.w);
       }
-      { QA_T0(); asm volatile("bar.sync 1, 512;" ::: "memory"); QA_ACC(6); }
+      { QA_T0(); asm volatile("bar.sync 1, 256;" ::: "memory"); QA_ACC(6); }
       const long long t_codes = PROF ? clock64() : 0;
-      // ---- pair codes of this thread's keys (block-invariant within the tile), branch-free:
+      const int w = tile * 2 + ws;
+      const bool valid = w < p.n_win && sl < L;
+      int64_t row;                                         // layout row of this thread's query
+      if (hat) row = (int64_t)w * L + sl;
+      else if (dil > 1) row = (int64_t)(w / dil) * K * dil + (int64_t)sl * dil + (w % dil);
+      else row = (int64_t)w * K + sl;
+      // ---- pair codes of the row (head-invariant, kept for the whole tile), branch-free:
       //      x | y << 10 | z << 20 byte offsets into the per-head-pair tables ----
-      const int4 me = s_tok[r];
+      const int4 me = s_tok[ws * 64 + sl];
       const bool row_norel = !use_rpe || (hat && sl == 0);
-      uint32_t code[KMAX];
+      uint32_t code[NKEY];
 #pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        const int key = k0 + j;                            // < 64 always
-        const int4 kj = s_tok[ws * 64 + key];
+      for (int j = 0; j < NKEY; ++j) {
+        const int4 kj = s_tok[ws * 64 + j];
         const int ox = min(max(me.x - kj.x, -bnd4), bnd4) + bnd4;
         const int oy = min(max(me.y - kj.y, -bnd4), bnd4) + bnd4;
         const int oz = min(max(me.z - kj.z, -bnd4), bnd4) + bnd4;
         const bool same = me.w == kj.w;
-        const bool norel = row_norel || (hat && key == 0);
+        const bool norel = row_norel || (hat && j == 0);
         uint32_t a = (uint32_t)ox | ((uint32_t)oy << 10) | ((uint32_t)oz << 20);
         if (norel) a = (uint32_t)o_zero | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
         if (!same) a = (uint32_t)o_inf | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
         code[j] = a;
       }
-      asm volatile("bar.sync 1, 512;" ::: "memory");      // s_tok may be rewritten for the next tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // s_tok may be rewritten for the next tile
       if (PROF) lacc[7] += clock64() - t_codes;
 
       for (int grp = 0; grp < G; ++grp, ++gcount) {
-        // ---- drain the QKV chunk: +bias, bf16, UMMA operand layouts; 12 units of 16 columns
-        //      (unit u: u / 4 = q | k | v, u % 4 = head of the group); part p takes q, k, v of head p ----
+        // ---- drain the QKV chunk: +bias, bf16, UMMA operand layouts.  Here lane r is row r of the y tile
+        //      (window yw = r / 64, slot sl).  12 units of 16 columns (u / 4 = q | k | v, u % 4 = head of the
+        //      group); the team takes q, k and v of the heads 2 team, 2 team + 1 ----
         { QA_T0(); ptx::mbar_wait(chunk_full, gcount & 1); QA_ACC(8); }
         if (gcount > 0) { QA_T0(); ptx::mbar_wait(attn_done, (gcount - 1) & 1); QA_ACC(9); }      // staging buffers free
         ptx::tc_fence_after();
         const long long t_drain2 = PROF ? clock64() : 0;
+        {
+          const int yw = r >> 6;
 #pragma unroll 1
-        for (int uu = 0; uu < 3; ++uu) {
-          const int u = uu * 4 + part, sect = uu, hl = part;   // part p: q, k and v of head p (balanced)
-          uint32_t raw[16];
-          ptx::tmem_ld16(lane_base + T_CHUNK + u * 16, raw);
-          ptx::tmem_ld_wait();
-          const float* bg = s_bias + grp * QA_GN + u * 16;
-          float v[16];
+          for (int i = 0; i < 6; ++i) {
+            const int sect = i >> 1, hl = team * 2 + (i & 1), dpar = hl & 1, dhp = hl >> 1;
+            const int u = sect * 4 + hl;
+            uint32_t raw[16];
+            ptx::tmem_ld16(lane_base + T_CHUNK + u * 16, raw);
+            ptx::tmem_ld_wait();
+            const float* bg = s_bias + grp * QA_GN + u * 16;
+            float v[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b = *reinterpret_cast<const float4*>(bg + 4 * q);
-            v[4 * q] = __uint_as_float(raw[4 * q]) + b.x;
-            v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
-            v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
-            v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
-          }
-          if (sect < 2) {
-            // row r of a K-major 128B-swizzled tile: 16-byte chunk ch at (ch ^ (r & 7)); head hl = chunks 2 hl, 2 hl + 1
-            const uint32_t rowa = (sect == 0 ? sQ : sK) + (uint32_t)r * 128u;
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = *reinterpret_cast<const float4*>(bg + 4 * q);
+              v[4 * q] = __uint_as_float(raw[4 * q]) + b.x;
+              v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+              v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+              v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+            }
+            if (sect < 2) {
+              // K-major 128B-swizzled tiles, 16-byte chunk ch of row rr at (ch ^ (rr & 7)).  Q: row
+              // (parity, slot) of the window's block-diagonal tile; K: row slot.  The head's 16 dims are the
+              // chunks 4 hp + 2 parity + {0, 1}: K columns hp * 32 + parity * 16 + d
+              const int rr = sect == 0 ? dpar * 64 + sl : sl;
+              const uint32_t rowa = (sect == 0 ? sA + (uint32_t)yw * 16384u : sK + (uint32_t)yw * 8192u) + (uint32_t)rr * 128u;
+              const int ch = dhp * 4 + dpar * 2;
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-              qa_sts128(rowa + (uint32_t)(((2 * hl + q) ^ (r & 7)) << 4), qa_pack(v[8 * q], v[8 * q + 1]),
-                        qa_pack(v[8 * q + 2], v[8 * q + 3]), qa_pack(v[8 * q + 4], v[8 * q + 5]),
-                        qa_pack(v[8 * q + 6], v[8 * q + 7]));
-          } else {
-            // V^T of head hl: element (dim d, key r) of a [16 x 128 B] K-major tile per 64 keys
-            const uint32_t keya = sV + (uint32_t)hl * 4096u + (uint32_t)(r >> 6) * 2048u + (uint32_t)(r & 7) * 2u;
-            const uint32_t kch = (uint32_t)(r & 63) >> 3;
+              for (int q = 0; q < 2; ++q)
+                qa_sts128(rowa + (uint32_t)(((ch + q) ^ (rr & 7)) << 4), qa_pack(v[8 * q], v[8 * q + 1]),
+                          qa_pack(v[8 * q + 2], v[8 * q + 3]), qa_pack(v[8 * q + 4], v[8 * q + 5]),
+                          qa_pack(v[8 * q + 6], v[8 * q + 7]));
+            } else {
+              // V^T of the (window, head pair): row n = parity * 16 + d, 64 keys = 128 B
+              const uint32_t keya = sV + (uint32_t)(yw * 2 + dhp) * 4096u + (uint32_t)(sl & 7) * 2u;
+              const uint32_t kch = (uint32_t)sl >> 3;
 #pragma unroll
-            for (int d = 0; d < 16; ++d) {
-              const __nv_bfloat16 hv = __float2bfloat16(v[d]);
-              qa_sts16(keya + (uint32_t)d * 128u + ((kch ^ (uint32_t)(d & 7)) << 4), *reinterpret_cast<const uint16_t*>(&hv));
+              for (int d = 0; d < 16; ++d) {
+                const __nv_bfloat16 hv = __float2bfloat16(v[d]);
+                const uint32_t n = (uint32_t)(dpar * 16 + d);
+                qa_sts16(keya + n * 128u + ((kch ^ (n & 7u)) << 4), *reinterpret_cast<const uint16_t*>(&hv));
+              }
             }
           }
         }
@@ -443,91 +448,119 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(qkv_ready);
         if (PROF) lacc[10] += clock64() - t_drain2;
-        // ---- the four heads of the group, one after the other; S / P buffers alternate ----
-        uint32_t bsum[KMAX];
+
+        // ---- softmax of the team's two units: heads grp * 4 + par (hp = 0) and grp * 4 + 2 + par (hp = 1) of
+        //      query (ws, sl); one table entry = the fp16 biases of exactly this pair of heads ----
+        const uint32_t tx = tab_u + (uint32_t)(((0 * G + grp) * 2 + par) * SUBP) * 4u;
+        const uint32_t ty = tab_u + (uint32_t)(((1 * G + grp) * 2 + par) * SUBP) * 4u;
+        const uint32_t tz = tab_u + (uint32_t)(((2 * G + grp) * 2 + par) * SUBP) * 4u;
+        uint32_t bs[NKEY];
+        float lsum[2];
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) bsum[j] = 0u;
-#pragma unroll 1
-        for (int hl = 0; hl < 4; ++hl, ++hcount) {
-          const int h = grp * 4 + hl;
-          const uint32_t buf = hl & 1;
-          const uint32_t t_s = lane_base + T_S + buf * 128u;
-          { QA_T0(); ptx::mbar_wait(s_full + 8 * buf, (hcount >> 1) & 1); QA_ACC(11); }
+        for (int hp = 0; hp < 2; ++hp) {
+          const int t = ws * 2 + hp, h = grp * 4 + hp * 2 + par;
+          const uint32_t t_u = lane_base + T_U + t * 64;
+          { QA_T0(); ptx::mbar_wait(s_full + 8 * t, gcount & 1); QA_ACC(11); }
           ptx::tc_fence_after();
           const long long t_sm = PROF ? clock64() : 0;
-          uint32_t raw[16];
-          ptx::tmem_ld16(t_s + ws * 64 + k0, raw);
-          ptx::tmem_ld_wait();
-          // shift for the exponent: an upper bound of the row maximum that needs no bias look-ups:
+          // pass 1: an upper bound of the row maximum that needs no bias look-ups:
           // max_j(raw) * sc + (largest table sum of the head)
-          float mx = __uint_as_float(raw[0]);
+          float mx = -INFINITY;
 #pragma unroll
-          for (int j = 1; j < KMAX; ++j) if (j < nk) mx = fmaxf(mx, __uint_as_float(raw[j]));
-          float* xch = s_mx + (hcount & 1) * 512;
-          xch[part * 128 + r] = mx;
-          // every part has its scores in registers behind this barrier: P may now overwrite S
-          asm volatile("bar.sync %0, 128;" ::"r"(2 + quad) : "memory");
-          mx = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
-          const float shift = fmaf(mx, sc, s_bmax[h]);
-          if ((hl & 1) == 0) {
-            // bias of every pair for this head AND the next one (fp16 pair per look-up), kept in registers
-            const int hp = h >> 1, Hh = H >> 1;
-            const uint32_t tx = tab_u + (uint32_t)(hp * SUBP) * 4u;
-            const uint32_t ty = tab_u + (uint32_t)((Hh + hp) * SUBP) * 4u;
-            const uint32_t tz = tab_u + (uint32_t)((2 * Hh + hp) * SUBP) * 4u;
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t raw[16];
+            if (c * 16 + 16 <= NKEY) qa_ld_cols<16>(t_u + c * 16, raw);
+            else qa_ld_cols<NKEY % 16 == 0 ? 16 : NKEY % 16>(t_u + c * 16, raw);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < KMAX; ++j) {
-              if (j < nk) {
-                const uint32_t cd = code[j];
-                bsum[j] = qa_hadd2(qa_hadd2(qa_lds_u32(tx + (cd & 0x3ffu)), qa_lds_u32(ty + ((cd >> 10) & 0x3ffu))),
-                                   qa_lds_u32(tz + (cd >> 20)));
-              }
-            }
+            for (int j = 0; j < 16; ++j) if (c * 16 + j < NKEY) mx = fmaxf(mx, __uint_as_float(raw[j]));
           }
+          const float nshift = -fmaf(mx, sc, s_bmax[h]);
+          // pass 2: p = 2^(s * sc + bias - shift), bf16 pairs along the keys back over the scores
           float l = 0.f;
-          uint32_t pk[(KMAX + 1) / 2];
 #pragma unroll
-          for (int j = 0; j < KMAX; j += 2) {
-            float pe[2] = {0.f, 0.f};
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t raw[16];
+            if (c * 16 + 16 <= NKEY) qa_ld_cols<16>(t_u + c * 16, raw);
+            else qa_ld_cols<NKEY % 16 == 0 ? 16 : NKEY % 16>(t_u + c * 16, raw);
+            if (hp == 0) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              if (j + e < KMAX && j + e < nk) {
-                const float b = (hl & 1) ? qa_half_hi(bsum[j + e]) : qa_half_lo(bsum[j + e]);
-                pe[e] = qa_ex2(fmaf(__uint_as_float(raw[j + e]), sc, b - shift));
+              for (int j = 0; j < 16; ++j)
+                if (c * 16 + j < NKEY) {
+                  const uint32_t cd = code[c * 16 + j];
+                  bs[c * 16 + j] = qa_hadd2(qa_hadd2(qa_lds_u32(tx + (cd & 0x3ffu)), qa_lds_u32(ty + ((cd >> 10) & 0x3ffu))),
+                                            qa_lds_u32(tz + (cd >> 20)));
+                }
+            }
+            ptx::tmem_ld_wait();
+            float pe[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pe[j] = 0.f;
+              if (c * 16 + j < NKEY) {
+                const float b = hp ? qa_half_hi(bs[c * 16 + j]) : qa_half_lo(bs[c * 16 + j]);
+                pe[j] = qa_ex2(fmaf(__uint_as_float(raw[j]), sc, b + nshift));
               }
             }
-            l += pe[0] + pe[1];
-            pk[j >> 1] = valid ? qa_pack(pe[0], pe[1]) : 0u;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              l += pe[2 * j] + pe[2 * j + 1];
+              pk[j] = valid ? qa_pack(pe[2 * j], pe[2 * j + 1]) : 0u;
+            }
+            ptx::tmem_st8(t_u + c * 8, pk);
           }
-          s_l[(hl * 4 + part) * 128 + r] = l;
-          // P (bf16 pairs along the keys) over the S buffer: this part's columns of the own window slot
-          // (the last part also clears the tail up to 64 keys) + a quarter of the other slot's zeros
-          {
-            const uint32_t pc = t_s + ws * 32 + part * (KP / 2);
-            if (part < 3) qa_st_cols<KP / 2>(pc, pk);
-            else qa_st_cols_tail<(KMAX + 1) / 2, 32 - 3 * (KP / 2)>(pc, pk);
-            uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            ptx::tmem_st8(t_s + (ws ^ 1) * 32 + part * 8, z);
-          }
+          lsum[hp] = l;
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(p_ready + 8 * buf);
+          if (lane == 0) ptx::mbar_arrive(p_ready + 8 * t);
           if (PROF) lacc[12] += clock64() - t_sm;
         }
-        drain_o(gcount, grp, row, valid);
+
+        // ---- outputs of the two units: O / rowsum -> bf16 -> global (32 B per row and head) ----
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          const int t = ws * 2 + hp, h = grp * 4 + hp * 2 + par;
+          const uint32_t t_u = lane_base + T_U + t * 64;
+          { QA_T0(); ptx::mbar_wait(o_full + 8 * t, gcount & 1); QA_ACC(13); }
+          ptx::tc_fence_after();
+          const long long t_od = PROF ? clock64() : 0;
+          uint32_t ro[16];
+          ptx::tmem_ld16(t_u + 32 + par * 16, ro);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(o_free + 8 * t);
+          if (valid) {
+            const float s = 1.0f / fmaxf(lsum[hp], 1e-37f);
+            uint4 a, b;
+            a.x = qa_pack(__uint_as_float(ro[0]) * s, __uint_as_float(ro[1]) * s);
+            a.y = qa_pack(__uint_as_float(ro[2]) * s, __uint_as_float(ro[3]) * s);
+            a.z = qa_pack(__uint_as_float(ro[4]) * s, __uint_as_float(ro[5]) * s);
+            a.w = qa_pack(__uint_as_float(ro[6]) * s, __uint_as_float(ro[7]) * s);
+            b.x = qa_pack(__uint_as_float(ro[8]) * s, __uint_as_float(ro[9]) * s);
+            b.y = qa_pack(__uint_as_float(ro[10]) * s, __uint_as_float(ro[11]) * s);
+            b.z = qa_pack(__uint_as_float(ro[12]) * s, __uint_as_float(ro[13]) * s);
+            b.w = qa_pack(__uint_as_float(ro[14]) * s, __uint_as_float(ro[15]) * s);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + row * C + h * 16);
+            dst[0] = a;
+            dst[1] = b;
+          }
+          if (PROF) lacc[14] += clock64() - t_od;
+        }
       }
     }
     if (PROF) lacc[15] = clock64() - t_role;
   }
   if (PROF && blockIdx.x == 0) {
-    if (threadIdx.x == 16 * 32) for (int i = 0; i < 6; ++i) p.prof[i] = lacc[i];
+    if (threadIdx.x == 8 * 32) for (int i = 0; i < 6; ++i) p.prof[i] = lacc[i];
     if (threadIdx.x == 0) for (int i = 6; i < 16; ++i) p.prof[i] = lacc[i];
-    if (threadIdx.x == 12 * 32) for (int i = 6; i < 16; ++i) p.prof[16 + i] = lacc[i];
+    if (threadIdx.x == 4 * 32) for (int i = 6; i < 16; ++i) p.prof[16 + i] = lacc[i];
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 16) {
+  if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -575,8 +608,8 @@ static int launch_qa(const CUtensorMap& ty, const CUtensorMap& tw, QaParams& p, 
     const int tiles = (p.n_win + 1) / 2, sms = sm_count();
     fprintf(stderr, "[hfl_qkv_attn prof n_win=%d tiles/CTA=%.1f]", p.n_win, (double)tiles / (tiles < sms ? tiles : sms));
     for (int i = 0; i < 6; ++i) fprintf(stderr, " %s=%.1fk", nm[i], h[i] / 1e3);
-    for (int i = 6; i < 16; ++i) fprintf(stderr, " p0:%s=%.1fk", nm[i], h[i] / 1e3);
-    for (int i = 6; i < 16; ++i) fprintf(stderr, " p3:%s=%.1fk", nm[i], h[16 + i] / 1e3);
+    for (int i = 6; i < 16; ++i) fprintf(stderr, " t0:%s=%.1fk", nm[i], h[i] / 1e3);
+    for (int i = 6; i < 16; ++i) fprintf(stderr, " t1:%s=%.1fk", nm[i], h[16 + i] / 1e3);
     fprintf(stderr, "\n");
     return rc;
   }
