@@ -102,6 +102,17 @@ __device__ __forceinline__ float qa_half_lo(uint32_t v) {
 __device__ __forceinline__ float qa_half_hi(uint32_t v) {
   return __half2float(__ushort_as_half((unsigned short)(v >> 16)));
 }
+// c + (fp16 half of a pair): mixed-precision add (FHADD), no separate conversion
+__device__ __forceinline__ float qa_fhadd_lo(uint32_t pair, float c) {
+  float d;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tadd.rn.f32.f16 %0, l, %2;\n\t}" : "=f"(d) : "r"(pair), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float qa_fhadd_hi(uint32_t pair, float c) {
+  float d;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tadd.rn.f32.f16 %0, h, %2;\n\t}" : "=f"(d) : "r"(pair), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float qa_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -146,13 +157,13 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
   const uint32_t bar = base + S::OFF_BAR;
   const uint32_t y_full = bar, y_empty = bar + 8;
   const uint32_t w_full = bar + 16, w_empty = bar + 16 + 8 * QA_RING;      // QA_RING each
-  const uint32_t chunk_full = bar + 64, qkv_ready = bar + 72, attn_done = bar + 80;
+  const uint32_t chunk_full = bar + 64, qk_ready = bar + 72, attn_done = bar + 80, v_ready = bar + 224;
   const uint32_t s_full = bar + 88;      // [4]  S of a unit is in tensor memory
   const uint32_t p_ready = bar + 120;    // [4]  P of a unit is in tensor memory
   const uint32_t o_full = bar + 152;     // [4]  O of a unit is in tensor memory
   const uint32_t o_free = bar + 184;     // [4]  O of a unit has been read: its buffer may take the next S
-  const uint32_t s_tmem = bar + 216;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 216);
+  const uint32_t s_tmem = bar + 232;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 232);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = p.K, hat = p.hat, L = K + hat, H = p.H, dil = p.dil;
@@ -191,7 +202,8 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     ptx::mbar_init(y_empty, 1);
     for (int s = 0; s < QA_RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
     ptx::mbar_init(chunk_full, 1);
-    ptx::mbar_init(qkv_ready, 8);
+    ptx::mbar_init(qk_ready, 8);
+    ptx::mbar_init(v_ready, 8);
     ptx::mbar_init(attn_done, 1);
     for (int t = 0; t < 4; ++t) {
       ptx::mbar_init(s_full + 8 * t, 1);
@@ -263,7 +275,7 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
       const uint32_t idesc_qkv = ptx::umma_idesc_bf16(128, QA_GN);
       const uint32_t idesc_s = ptx::umma_idesc_bf16(128, 64);
       const uint32_t idesc_pv = ptx::umma_idesc_bf16(128, 32);
-      uint32_t ring = 0, gcount = 0;
+      uint32_t ring = 0;
       auto issue_qkv = [&](int grp) {
         for (int kb = 0; kb < KB; ++kb, ++ring) {
           const uint32_t s = ring % QA_RING, ph = (ring / QA_RING) & 1;
@@ -279,51 +291,57 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
         ptx::umma_commit(chunk_full);
         if (grp == G - 1) ptx::umma_commit(y_empty);
       };
-      bool first_issued = false;                           // chunk 0 of this tile was issued during the previous tile
-      for (int it = 0; it < n_my; ++it) {
-        if (!first_issued) {
-          { QA_T0(); ptx::mbar_wait(y_full, it & 1); QA_ACC(1); }
+      // Flat loop over (tile, head group).  Per group: S of the four units as soon as Q / K are staged and the
+      // units' buffers were emptied -> the next projection chunk as soon as V^T is staged too (the chunk columns
+      // are free then) -> the PV products in the order the teams deliver P.
+      const int total = n_my * G;
+      { QA_T0(); ptx::mbar_wait(y_full, 0); QA_ACC(1); }
+      ptx::tc_fence_after();
+      issue_qkv(0);
+      for (int gi = 0; gi < total; ++gi) {
+        const int it = gi / G, grp = gi - it * G;
+        const uint32_t ph = gi & 1;
+        { QA_T0(); ptx::mbar_wait(qk_ready, ph); QA_ACC(2); }      // Q / K of this group are in shared memory
+        // unit t = (window ws = t / 2, head pair hp = t % 2): S[(parity, query)][key] for both heads of the
+        // pair in ONE accumulator through the block-diagonal Q tile (K = 32: 16 dims x 2 heads)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int ws = t >> 1, hp = t & 1;
+          if (gi > 0) { QA_T0(); ptx::mbar_wait(o_free + 8 * t, ph ^ 1); QA_ACC(4); }
+          ptx::tc_fence_after();
+          const uint64_t ad = ptx::umma_desc_sw128(sA + ws * 16384) + 4 * hp;
+          const uint64_t bd = ptx::umma_desc_sw128(sK + ws * 8192) + 4 * hp;
+          ptx::umma_bf16(tmem_base + T_U + t * 64, ad, bd, idesc_s, 0);
+          ptx::umma_bf16(tmem_base + T_U + t * 64, ad + 2, bd + 2, idesc_s, 1);
+          ptx::umma_commit(s_full + 8 * t);
+        }
+        { QA_T0(); ptx::mbar_wait(v_ready, ph); QA_ACC(2); }       // V^T staged: the chunk columns are free
+        ptx::tc_fence_after();
+        // next projection chunk; across the tile boundary only if the next y tile has already landed (never
+        // stall the PV issue on it), otherwise after the PV products
+        bool deferred = false;
+        if (gi + 1 < total) {
+          if (grp + 1 < G) issue_qkv(grp + 1);
+          else if (ptx::mbar_try_wait(y_full, (it + 1) & 1)) { ptx::tc_fence_after(); issue_qkv(0); }
+          else deferred = true;
+        }
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const int t = (tt & 1) * 2 + (tt >> 1);          // the order the teams finish them: 0, 2, 1, 3
+          { QA_T0(); ptx::mbar_wait(p_ready + 8 * t, ph); QA_ACC(3); }
+          ptx::tc_fence_after();
+          const uint64_t vd = ptx::umma_desc_sw128(sV + t * 4096);
+#pragma unroll
+          for (int kk = 0; kk < NCH; ++kk)
+            ptx::umma_bf16_ts(tmem_base + T_U + t * 64 + 32, tmem_base + T_U + t * 64 + 8 * kk, vd + 2 * kk,
+                              idesc_pv, kk != 0);
+          ptx::umma_commit(o_full + 8 * t);
+        }
+        ptx::umma_commit(attn_done);
+        if (deferred) {
+          { QA_T0(); ptx::mbar_wait(y_full, (it + 1) & 1); QA_ACC(1); }
           ptx::tc_fence_after();
           issue_qkv(0);
-        }
-        first_issued = false;
-        for (int grp = 0; grp < G; ++grp, ++gcount) {
-          { QA_T0(); ptx::mbar_wait(qkv_ready, gcount & 1); QA_ACC(2); }   // Q / K / V^T of this group are in shared memory
-          ptx::tc_fence_after();
-          // unit t = (window ws = t / 2, head pair hp = t % 2): S[(parity, query)][key] for both heads of the
-          // pair in ONE accumulator through the block-diagonal Q tile (K = 32: 16 dims x 2 heads)
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int ws = t >> 1, hp = t & 1;
-            if (gcount > 0) { QA_T0(); ptx::mbar_wait(o_free + 8 * t, (gcount - 1) & 1); QA_ACC(4); }
-            ptx::tc_fence_after();
-            const uint64_t ad = ptx::umma_desc_sw128(sA + ws * 16384) + 4 * hp;
-            const uint64_t bd = ptx::umma_desc_sw128(sK + ws * 8192) + 4 * hp;
-            ptx::umma_bf16(tmem_base + T_U + t * 64, ad, bd, idesc_s, 0);
-            ptx::umma_bf16(tmem_base + T_U + t * 64, ad + 2, bd + 2, idesc_s, 1);
-            ptx::umma_commit(s_full + 8 * t);
-          }
-          // next projection chunk (the chunk columns were drained before qkv_ready); across the tile boundary
-          // only if the next y tile has already landed (never stall the PV issue on it)
-          if (grp + 1 < G) issue_qkv(grp + 1);
-          else if (it + 1 < n_my && ptx::mbar_try_wait(y_full, (it + 1) & 1)) {
-            ptx::tc_fence_after();
-            issue_qkv(0);
-            first_issued = true;
-          }
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            const int t = (tt & 1) * 2 + (tt >> 1);          // the order the teams finish them: 0, 2, 1, 3
-            { QA_T0(); ptx::mbar_wait(p_ready + 8 * t, gcount & 1); QA_ACC(3); }
-            ptx::tc_fence_after();
-            const uint64_t vd = ptx::umma_desc_sw128(sV + t * 4096);
-#pragma unroll
-            for (int kk = 0; kk < NCH; ++kk)
-              ptx::umma_bf16_ts(tmem_base + T_U + t * 64 + 32, tmem_base + T_U + t * 64 + 8 * kk, vd + 2 * kk,
-                                idesc_pv, kk != 0);
-            ptx::umma_commit(o_full + 8 * t);
-          }
-          ptx::umma_commit(attn_done);
         }
       }
       if (PROF) lacc[5] = clock64() - t_role;
@@ -346,209 +364,247 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     const uint32_t tab_u = base + S::OFF_TAB;
     const int o_zero = num * 4, o_inf = (num + 1) * 4;
     const int bnd4 = p.bnd * 4;
-    uint32_t gcount = 0;
-
-    for (int it = 0; it < n_my; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      // token table of the tile: thread r of team 0 loads the token of y-tile row r (window r / 64, slot r % 64)
-      if (team == 0) {
-        const int w0 = tile * 2 + (r >> 6);
-        const bool v0 = w0 < p.n_win && sl < L;
-        int64_t tok0;
-        if (hat) tok0 = (int64_t)w0 * K + (sl == 0 ? 0 : sl - 1);
-        else if (dil > 1) tok0 = (int64_t)(w0 / dil) * K * dil + (int64_t)sl * dil + (w0 % dil);
-        else tok0 = (int64_t)w0 * K + sl;
-        // coordinates pre-multiplied by 4: clamp(4 dx, +-4 bnd) + 4 bnd is the byte offset into a table of 4-byte entries
-        const short4 tk = v0 ? __ldg(p.xyzb + tok0) : make_short4(0, 0, 0, -2);
-        s_tok[r] = make_int4(4 * (int)tk.x, 4 * (int)tk.y, 4 * (int)tk.z, (int)tk.w);
-      }
-      { QA_T0(); asm volatile("bar.sync 1, 256;" ::: "memory"); QA_ACC(6); }
-      const long long t_codes = PROF ? clock64() : 0;
-      const int w = tile * 2 + ws;
-      const bool valid = w < p.n_win && sl < L;
-      int64_t row;                                         // layout row of this thread's query
-      if (hat) row = (int64_t)w * L + sl;
-      else if (dil > 1) row = (int64_t)(w / dil) * K * dil + (int64_t)sl * dil + (w % dil);
-      else row = (int64_t)w * K + sl;
-      // ---- pair codes of the row (head-invariant, kept for the whole tile), branch-free:
-      //      x | y << 10 | z << 20 byte offsets into the per-head-pair tables ----
-      const int4 me = s_tok[ws * 64 + sl];
-      const bool row_norel = !use_rpe || (hat && sl == 0);
-      uint32_t code[NKEY];
+    const int total = n_my * G;
+    const int yw = r >> 6;                                 // drain view of the lane: row r of the y tile
+    // +bias, bf16, UMMA operand layouts for one 16-column unit of the QKV chunk of group `grp` (u / 4 =
+    // q | k | v, u % 4 = head hl of the group).  Here lane r is row r of the y tile (window yw, slot sl).
+    auto drain_unit = [&](int grp, int sect, int hl) {
+      const int dpar = hl & 1, dhp = hl >> 1, u = sect * 4 + hl;
+      uint32_t raw[16];
+      ptx::tmem_ld16(lane_base + T_CHUNK + u * 16, raw);
+      ptx::tmem_ld_wait();
+      const float* bg = s_bias + grp * QA_GN + u * 16;
+      float v[16];
 #pragma unroll
-      for (int j = 0; j < NKEY; ++j) {
-        const int4 kj = s_tok[ws * 64 + j];
-        const int ox = min(max(me.x - kj.x, -bnd4), bnd4) + bnd4;
-        const int oy = min(max(me.y - kj.y, -bnd4), bnd4) + bnd4;
-        const int oz = min(max(me.z - kj.z, -bnd4), bnd4) + bnd4;
-        const bool same = me.w == kj.w;
-        const bool norel = row_norel || (hat && j == 0);
-        uint32_t a = (uint32_t)ox | ((uint32_t)oy << 10) | ((uint32_t)oz << 20);
-        if (norel) a = (uint32_t)o_zero | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
-        if (!same) a = (uint32_t)o_inf | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
-        code[j] = a;
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(bg + 4 * q);
+        v[4 * q] = __uint_as_float(raw[4 * q]) + b.x;
+        v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
+        v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
+        v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // s_tok may be rewritten for the next tile
-      if (PROF) lacc[7] += clock64() - t_codes;
-
-      for (int grp = 0; grp < G; ++grp, ++gcount) {
-        // ---- drain the QKV chunk: +bias, bf16, UMMA operand layouts.  Here lane r is row r of the y tile
-        //      (window yw = r / 64, slot sl).  12 units of 16 columns (u / 4 = q | k | v, u % 4 = head of the
-        //      group); the team takes q, k and v of the heads 2 team, 2 team + 1 ----
-        { QA_T0(); ptx::mbar_wait(chunk_full, gcount & 1); QA_ACC(8); }
-        if (gcount > 0) { QA_T0(); ptx::mbar_wait(attn_done, (gcount - 1) & 1); QA_ACC(9); }      // staging buffers free
-        ptx::tc_fence_after();
-        const long long t_drain2 = PROF ? clock64() : 0;
-        {
-          const int yw = r >> 6;
+      if (sect < 2) {
+        // K-major 128B-swizzled tiles, 16-byte chunk ch of row rr at (ch ^ (rr & 7)).  Q: row (parity, slot) of
+        // the window's block-diagonal tile; K: row slot.  The head's 16 dims are the chunks
+        // 4 hp + 2 parity + {0, 1}: K columns hp * 32 + parity * 16 + d
+        const int rr = sect == 0 ? dpar * 64 + sl : sl;
+        const uint32_t rowa = (sect == 0 ? sA + (uint32_t)yw * 16384u : sK + (uint32_t)yw * 8192u) + (uint32_t)rr * 128u;
+        const int ch = dhp * 4 + dpar * 2;
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          qa_sts128(rowa + (uint32_t)(((ch + q) ^ (rr & 7)) << 4), qa_pack(v[8 * q], v[8 * q + 1]),
+                    qa_pack(v[8 * q + 2], v[8 * q + 3]), qa_pack(v[8 * q + 4], v[8 * q + 5]),
+                    qa_pack(v[8 * q + 6], v[8 * q + 7]));
+      } else {
+        // V^T of the (window, head pair): row n = parity * 16 + d, 64 keys = 128 B
+        const uint32_t keya = sV + (uint32_t)(yw * 2 + dhp) * 4096u + (uint32_t)(sl & 7) * 2u;
+        const uint32_t kch = (uint32_t)sl >> 3;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          const __nv_bfloat16 hv = __float2bfloat16(v[d]);
+          const uint32_t n = (uint32_t)(dpar * 16 + d);
+          qa_sts16(keya + n * 128u + ((kch ^ (n & 7u)) << 4), *reinterpret_cast<const uint16_t*>(&hv));
+        }
+      }
+    };
+    // the team takes q, k and v of the heads 2 team, 2 team + 1 of the group
+    auto drain_qk = [&](int gi) {
+      const long long t_d = PROF ? clock64() : 0;
+      const int grp = gi % G;
 #pragma unroll 1
-          for (int i = 0; i < 6; ++i) {
-            const int sect = i >> 1, hl = team * 2 + (i & 1), dpar = hl & 1, dhp = hl >> 1;
-            const int u = sect * 4 + hl;
-            uint32_t raw[16];
-            ptx::tmem_ld16(lane_base + T_CHUNK + u * 16, raw);
-            ptx::tmem_ld_wait();
-            const float* bg = s_bias + grp * QA_GN + u * 16;
-            float v[16];
+      for (int i = 0; i < 4; ++i) drain_unit(grp, i >> 1, team * 2 + (i & 1));
+      ptx::fence_proxy_async();                            // generic-proxy stores -> UMMA (async proxy)
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(qk_ready);
+      if (PROF) lacc[10] += clock64() - t_d;
+    };
+    auto drain_v = [&](int gi) {
+      const long long t_d = PROF ? clock64() : 0;
+      const int grp = gi % G;
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) drain_unit(grp, 2, team * 2 + i);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(v_ready);
+      if (PROF) lacc[10] += clock64() - t_d;
+    };
+
+    // prologue: stage group 0 of the first tile
+    if (total > 0) {
+      { QA_T0(); ptx::mbar_wait(chunk_full, 0); QA_ACC(8); }
+      ptx::tc_fence_after();
+      drain_qk(0);
+      drain_v(0);
+    }
+    uint32_t code[NKEY];
+    bool valid = false;
+    int64_t row = 0;
+    for (int gi = 0; gi < total; ++gi) {
+      const int it = gi / G, grp = gi - it * G;
+      const uint32_t gcount = (uint32_t)gi;
+      if (grp == 0) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        // token table of the tile: thread r of team 0 loads the token of y-tile row r (window r / 64, slot r % 64)
+        if (team == 0) {
+          const int w0 = tile * 2 + (r >> 6);
+          const bool v0 = w0 < p.n_win && sl < L;
+          int64_t tok0;
+          if (hat) tok0 = (int64_t)w0 * K + (sl == 0 ? 0 : sl - 1);
+          else if (dil > 1) tok0 = (int64_t)(w0 / dil) * K * dil + (int64_t)sl * dil + (w0 % dil);
+          else tok0 = (int64_t)w0 * K + sl;
+          // coordinates pre-multiplied by 4: clamp(4 dx, +-4 bnd) + 4 bnd is the byte offset into a table of 4-byte entries
+          const short4 tk = v0 ? __ldg(p.xyzb + tok0) : make_short4(0, 0, 0, -2);
+          s_tok[r] = make_int4(4 * (int)tk.x, 4 * (int)tk.y, 4 * (int)tk.z, (int)tk.w);
+        }
+        { QA_T0(); asm volatile("bar.sync 1, 256;" ::: "memory"); QA_ACC(6); }
+        const long long t_codes = PROF ? clock64() : 0;
+        const int w = tile * 2 + ws;
+        valid = w < p.n_win && sl < L;
+        if (hat) row = (int64_t)w * L + sl;
+        else if (dil > 1) row = (int64_t)(w / dil) * K * dil + (int64_t)sl * dil + (w % dil);
+        else row = (int64_t)w * K + sl;
+        // ---- pair codes of the row (head-invariant, kept for the whole tile), branch-free:
+        //      x | y << 10 | z << 20 byte offsets into the per-head-pair tables ----
+        const int4 me = s_tok[ws * 64 + sl];
+        const bool row_norel = !use_rpe || (hat && sl == 0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b = *reinterpret_cast<const float4*>(bg + 4 * q);
-              v[4 * q] = __uint_as_float(raw[4 * q]) + b.x;
-              v[4 * q + 1] = __uint_as_float(raw[4 * q + 1]) + b.y;
-              v[4 * q + 2] = __uint_as_float(raw[4 * q + 2]) + b.z;
-              v[4 * q + 3] = __uint_as_float(raw[4 * q + 3]) + b.w;
+        for (int j = 0; j < NKEY; ++j) {
+          const int4 kj = s_tok[ws * 64 + j];
+          const int ox = min(max(me.x - kj.x, -bnd4), bnd4) + bnd4;
+          const int oy = min(max(me.y - kj.y, -bnd4), bnd4) + bnd4;
+          const int oz = min(max(me.z - kj.z, -bnd4), bnd4) + bnd4;
+          const bool same = me.w == kj.w;
+          const bool norel = row_norel || (hat && j == 0);
+          uint32_t a = (uint32_t)ox | ((uint32_t)oy << 10) | ((uint32_t)oz << 20);
+          if (norel) a = (uint32_t)o_zero | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
+          if (!same) a = (uint32_t)o_inf | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
+          code[j] = a;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // s_tok may be rewritten for the next tile
+        if (PROF) lacc[7] += clock64() - t_codes;
+
+      }
+      // ---- softmax of the team's two units TOGETHER: heads grp * 4 + par (unit 0) and grp * 4 + 2 + par
+      //      (unit 1) of query (ws, sl); one table entry = the fp16 biases of exactly this pair of heads, so
+      //      a (query, key) pair costs three look-ups for both units and nothing is cached ----
+      const uint32_t tx = tab_u + (uint32_t)(((0 * G + grp) * 2 + par) * SUBP) * 4u;
+      const uint32_t ty = tab_u + (uint32_t)(((1 * G + grp) * 2 + par) * SUBP) * 4u;
+      const uint32_t tz = tab_u + (uint32_t)(((2 * G + grp) * 2 + par) * SUBP) * 4u;
+      const uint32_t t_u0 = lane_base + T_U + (ws * 2) * 64, t_u1 = t_u0 + 64;
+      float lsum[2];
+      {
+        { QA_T0(); ptx::mbar_wait(s_full + 8 * (ws * 2), gcount & 1); ptx::mbar_wait(s_full + 8 * (ws * 2 + 1), gcount & 1); QA_ACC(11); }
+        ptx::tc_fence_after();
+        const long long t_sm = PROF ? clock64() : 0;
+        constexpr int NLAST = NKEY - (NCH - 1) * 16;        // keys of the last chunk (1 .. 16)
+        uint32_t raw[2][2][16];                              // [buffer][unit][key of the chunk]
+        auto load_chunk = [&](int c, uint32_t (&dst)[2][16]) {
+          if (c < NCH - 1) { qa_ld_cols<16>(t_u0 + c * 16, dst[0]); qa_ld_cols<16>(t_u1 + c * 16, dst[1]); }
+          else { qa_ld_cols<NLAST>(t_u0 + c * 16, dst[0]); qa_ld_cols<NLAST>(t_u1 + c * 16, dst[1]); }
+        };
+        // pass 1: an upper bound of the row maxima that needs no bias look-ups:
+        // max_j(raw) * sc + (largest table sum of the head)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        load_chunk(0, raw[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < NCH) load_chunk(c + 1, raw[(c + 1) & 1]);
+          else load_chunk(0, raw[(c + 1) & 1]);              // first chunk of pass 2
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c * 16 + j < NKEY) {
+              mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][0][j]));
+              mx1 = fmaxf(mx1, __uint_as_float(raw[c & 1][1][j]));
             }
-            if (sect < 2) {
-              // K-major 128B-swizzled tiles, 16-byte chunk ch of row rr at (ch ^ (rr & 7)).  Q: row
-              // (parity, slot) of the window's block-diagonal tile; K: row slot.  The head's 16 dims are the
-              // chunks 4 hp + 2 parity + {0, 1}: K columns hp * 32 + parity * 16 + d
-              const int rr = sect == 0 ? dpar * 64 + sl : sl;
-              const uint32_t rowa = (sect == 0 ? sA + (uint32_t)yw * 16384u : sK + (uint32_t)yw * 8192u) + (uint32_t)rr * 128u;
-              const int ch = dhp * 4 + dpar * 2;
+        }
+        const int h0 = grp * 4 + par;
+        const float nshift0 = -fmaf(mx0, sc, s_bmax[h0]), nshift1 = -fmaf(mx1, sc, s_bmax[h0 + 2]);
+        // pass 2: p = 2^(s * sc + bias - shift), bf16 pairs along the keys back over the scores
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-              for (int q = 0; q < 2; ++q)
-                qa_sts128(rowa + (uint32_t)(((ch + q) ^ (rr & 7)) << 4), qa_pack(v[8 * q], v[8 * q + 1]),
-                          qa_pack(v[8 * q + 2], v[8 * q + 3]), qa_pack(v[8 * q + 4], v[8 * q + 5]),
-                          qa_pack(v[8 * q + 6], v[8 * q + 7]));
-            } else {
-              // V^T of the (window, head pair): row n = parity * 16 + d, 64 keys = 128 B
-              const uint32_t keya = sV + (uint32_t)(yw * 2 + dhp) * 4096u + (uint32_t)(sl & 7) * 2u;
-              const uint32_t kch = (uint32_t)sl >> 3;
+        for (int c = 0; c < NCH; ++c) {
+          const int bi = (NCH + c) & 1;                      // buffer the chunk was loaded into
+          ptx::tmem_ld_wait();
+          if (c + 1 < NCH) load_chunk(c + 1, raw[bi ^ 1]);
+          float pe0[16], pe1[16];
 #pragma unroll
-              for (int d = 0; d < 16; ++d) {
-                const __nv_bfloat16 hv = __float2bfloat16(v[d]);
-                const uint32_t n = (uint32_t)(dpar * 16 + d);
-                qa_sts16(keya + n * 128u + ((kch ^ (n & 7u)) << 4), *reinterpret_cast<const uint16_t*>(&hv));
-              }
+          for (int j = 0; j < 16; ++j) {
+            pe0[j] = pe1[j] = 0.f;
+            if (c * 16 + j < NKEY) {
+              const uint32_t cd = code[c * 16 + j];
+              const uint32_t bs = qa_hadd2(qa_hadd2(qa_lds_u32(tx + (cd & 0x3ffu)), qa_lds_u32(ty + ((cd >> 10) & 0x3ffu))),
+                                           qa_lds_u32(tz + (cd >> 20)));
+              pe0[j] = qa_ex2(qa_fhadd_lo(bs, fmaf(__uint_as_float(raw[bi][0][j]), sc, nshift0)));
+              pe1[j] = qa_ex2(qa_fhadd_hi(bs, fmaf(__uint_as_float(raw[bi][1][j]), sc, nshift1)));
             }
           }
+          uint32_t pk0[8], pk1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            l0 += pe0[2 * j] + pe0[2 * j + 1];
+            l1 += pe1[2 * j] + pe1[2 * j + 1];
+            pk0[j] = valid ? qa_pack(pe0[2 * j], pe0[2 * j + 1]) : 0u;
+            pk1[j] = valid ? qa_pack(pe1[2 * j], pe1[2 * j + 1]) : 0u;
+          }
+          ptx::tmem_st8(t_u0 + c * 8, pk0);
+          ptx::tmem_st8(t_u1 + c * 8, pk1);
         }
-        ptx::fence_proxy_async();                          // generic-proxy stores -> UMMA (async proxy)
+        lsum[0] = l0;
+        lsum[1] = l1;
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(qkv_ready);
-        if (PROF) lacc[10] += clock64() - t_drain2;
+        if (lane == 0) { ptx::mbar_arrive(p_ready + 8 * (ws * 2)); ptx::mbar_arrive(p_ready + 8 * (ws * 2 + 1)); }
+        if (PROF) lacc[12] += clock64() - t_sm;
+      }
 
-        // ---- softmax of the team's two units: heads grp * 4 + par (hp = 0) and grp * 4 + 2 + par (hp = 1) of
-        //      query (ws, sl); one table entry = the fp16 biases of exactly this pair of heads ----
-        const uint32_t tx = tab_u + (uint32_t)(((0 * G + grp) * 2 + par) * SUBP) * 4u;
-        const uint32_t ty = tab_u + (uint32_t)(((1 * G + grp) * 2 + par) * SUBP) * 4u;
-        const uint32_t tz = tab_u + (uint32_t)(((2 * G + grp) * 2 + par) * SUBP) * 4u;
-        uint32_t bs[NKEY];
-        float lsum[2];
+      // ---- while the PV products run: stage Q / K of the next group (S of this group has been read by every
+      //      team's softmax only after ALL four S products completed -- they complete in issue order) ----
+      if (gi + 1 < total) {
+        { QA_T0(); ptx::mbar_wait(chunk_full, (gcount + 1) & 1); QA_ACC(8); }
+        { QA_T0(); ptx::mbar_wait(s_full + 8 * 3, gcount & 1); QA_ACC(9); }
+        ptx::tc_fence_after();
+        drain_qk(gi + 1);
+      }
+      // ---- outputs of the two units: O / rowsum -> bf16 -> global (32 B per row and head) ----
 #pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          const int t = ws * 2 + hp, h = grp * 4 + hp * 2 + par;
-          const uint32_t t_u = lane_base + T_U + t * 64;
-          { QA_T0(); ptx::mbar_wait(s_full + 8 * t, gcount & 1); QA_ACC(11); }
-          ptx::tc_fence_after();
-          const long long t_sm = PROF ? clock64() : 0;
-          // pass 1: an upper bound of the row maximum that needs no bias look-ups:
-          // max_j(raw) * sc + (largest table sum of the head)
-          float mx = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t raw[16];
-            if (c * 16 + 16 <= NKEY) qa_ld_cols<16>(t_u + c * 16, raw);
-            else qa_ld_cols<NKEY % 16 == 0 ? 16 : NKEY % 16>(t_u + c * 16, raw);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) if (c * 16 + j < NKEY) mx = fmaxf(mx, __uint_as_float(raw[j]));
-          }
-          const float nshift = -fmaf(mx, sc, s_bmax[h]);
-          // pass 2: p = 2^(s * sc + bias - shift), bf16 pairs along the keys back over the scores
-          float l = 0.f;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t raw[16];
-            if (c * 16 + 16 <= NKEY) qa_ld_cols<16>(t_u + c * 16, raw);
-            else qa_ld_cols<NKEY % 16 == 0 ? 16 : NKEY % 16>(t_u + c * 16, raw);
-            if (hp == 0) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c * 16 + j < NKEY) {
-                  const uint32_t cd = code[c * 16 + j];
-                  bs[c * 16 + j] = qa_hadd2(qa_hadd2(qa_lds_u32(tx + (cd & 0x3ffu)), qa_lds_u32(ty + ((cd >> 10) & 0x3ffu))),
-                                            qa_lds_u32(tz + (cd >> 20)));
-                }
-            }
-            ptx::tmem_ld_wait();
-            float pe[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              pe[j] = 0.f;
-              if (c * 16 + j < NKEY) {
-                const float b = hp ? qa_half_hi(bs[c * 16 + j]) : qa_half_lo(bs[c * 16 + j]);
-                pe[j] = qa_ex2(fmaf(__uint_as_float(raw[j]), sc, b + nshift));
-              }
-            }
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              l += pe[2 * j] + pe[2 * j + 1];
-              pk[j] = valid ? qa_pack(pe[2 * j], pe[2 * j + 1]) : 0u;
-            }
-            ptx::tmem_st8(t_u + c * 8, pk);
-          }
-          lsum[hp] = l;
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(p_ready + 8 * t);
-          if (PROF) lacc[12] += clock64() - t_sm;
+      for (int hp = 0; hp < 2; ++hp) {
+        const int t = ws * 2 + hp, h = grp * 4 + hp * 2 + par;
+        const uint32_t t_u = lane_base + T_U + t * 64;
+        { QA_T0(); ptx::mbar_wait(o_full + 8 * t, gcount & 1); QA_ACC(13); }
+        ptx::tc_fence_after();
+        const long long t_od = PROF ? clock64() : 0;
+        uint32_t ro[16];
+        ptx::tmem_ld16(t_u + 32 + par * 16, ro);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(o_free + 8 * t);
+        if (valid) {
+          const float s = 1.0f / fmaxf(lsum[hp], 1e-37f);
+          uint4 a, b;
+          a.x = qa_pack(__uint_as_float(ro[0]) * s, __uint_as_float(ro[1]) * s);
+          a.y = qa_pack(__uint_as_float(ro[2]) * s, __uint_as_float(ro[3]) * s);
+          a.z = qa_pack(__uint_as_float(ro[4]) * s, __uint_as_float(ro[5]) * s);
+          a.w = qa_pack(__uint_as_float(ro[6]) * s, __uint_as_float(ro[7]) * s);
+          b.x = qa_pack(__uint_as_float(ro[8]) * s, __uint_as_float(ro[9]) * s);
+          b.y = qa_pack(__uint_as_float(ro[10]) * s, __uint_as_float(ro[11]) * s);
+          b.z = qa_pack(__uint_as_float(ro[12]) * s, __uint_as_float(ro[13]) * s);
+          b.w = qa_pack(__uint_as_float(ro[14]) * s, __uint_as_float(ro[15]) * s);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + row * C + h * 16);
+          dst[0] = a;
+          dst[1] = b;
         }
-
-        // ---- outputs of the two units: O / rowsum -> bf16 -> global (32 B per row and head) ----
-#pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          const int t = ws * 2 + hp, h = grp * 4 + hp * 2 + par;
-          const uint32_t t_u = lane_base + T_U + t * 64;
-          { QA_T0(); ptx::mbar_wait(o_full + 8 * t, gcount & 1); QA_ACC(13); }
-          ptx::tc_fence_after();
-          const long long t_od = PROF ? clock64() : 0;
-          uint32_t ro[16];
-          ptx::tmem_ld16(t_u + 32 + par * 16, ro);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(o_free + 8 * t);
-          if (valid) {
-            const float s = 1.0f / fmaxf(lsum[hp], 1e-37f);
-            uint4 a, b;
-            a.x = qa_pack(__uint_as_float(ro[0]) * s, __uint_as_float(ro[1]) * s);
-            a.y = qa_pack(__uint_as_float(ro[2]) * s, __uint_as_float(ro[3]) * s);
-            a.z = qa_pack(__uint_as_float(ro[4]) * s, __uint_as_float(ro[5]) * s);
-            a.w = qa_pack(__uint_as_float(ro[6]) * s, __uint_as_float(ro[7]) * s);
-            b.x = qa_pack(__uint_as_float(ro[8]) * s, __uint_as_float(ro[9]) * s);
-            b.y = qa_pack(__uint_as_float(ro[10]) * s, __uint_as_float(ro[11]) * s);
-            b.z = qa_pack(__uint_as_float(ro[12]) * s, __uint_as_float(ro[13]) * s);
-            b.w = qa_pack(__uint_as_float(ro[14]) * s, __uint_as_float(ro[15]) * s);
-            uint4* dst = reinterpret_cast<uint4*>(p.out + row * C + h * 16);
-            dst[0] = a;
-            dst[1] = b;
-          }
-          if (PROF) lacc[14] += clock64() - t_od;
-        }
+        if (PROF) lacc[14] += clock64() - t_od;
+      }
+      // ---- V^T of the next group once every PV product of this one has completed ----
+      if (gi + 1 < total) {
+        { QA_T0(); ptx::mbar_wait(attn_done, gcount & 1); QA_ACC(9); }
+        ptx::tc_fence_after();
+        drain_v(gi + 1);
       }
     }
     if (PROF) lacc[15] = clock64() - t_role;
