@@ -498,59 +498,67 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
         { QA_T0(); ptx::mbar_wait(s_full + 8 * (ws * 2), gcount & 1); ptx::mbar_wait(s_full + 8 * (ws * 2 + 1), gcount & 1); QA_ACC(11); }
         ptx::tc_fence_after();
         const long long t_sm = PROF ? clock64() : 0;
-        constexpr int NLAST = NKEY - (NCH - 1) * 16;        // keys of the last chunk (1 .. 16)
-        uint32_t raw[2][2][16];                              // [buffer][unit][key of the chunk]
-        auto load_chunk = [&](int c, uint32_t (&dst)[2][16]) {
-          if (c < NCH - 1) { qa_ld_cols<16>(t_u0 + c * 16, dst[0]); qa_ld_cols<16>(t_u1 + c * 16, dst[1]); }
-          else { qa_ld_cols<NLAST>(t_u0 + c * 16, dst[0]); qa_ld_cols<NLAST>(t_u1 + c * 16, dst[1]); }
+        constexpr int NC8 = (NKEY + 7) / 8;                  // 8-key chunks of a row
+        constexpr int NLAST = NKEY - (NC8 - 1) * 8;          // keys of the last chunk (1 .. 8)
+        uint32_t raw[2][2][8];                               // [buffer][unit][key of the chunk]: the next chunk is in flight
+        auto load_chunk = [&](int c, uint32_t (&dst)[2][8]) {
+          if (c < NC8 - 1) { qa_ld_cols<8>(t_u0 + c * 8, dst[0]); qa_ld_cols<8>(t_u1 + c * 8, dst[1]); }
+          else { qa_ld_cols<NLAST>(t_u0 + c * 8, dst[0]); qa_ld_cols<NLAST>(t_u1 + c * 8, dst[1]); }
         };
         // pass 1: an upper bound of the row maxima that needs no bias look-ups:
         // max_j(raw) * sc + (largest table sum of the head)
         float mx0 = -INFINITY, mx1 = -INFINITY;
         load_chunk(0, raw[0]);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = 0; c < NC8; ++c) {
           ptx::tmem_ld_wait();
-          if (c + 1 < NCH) load_chunk(c + 1, raw[(c + 1) & 1]);
+          if (c + 1 < NC8) load_chunk(c + 1, raw[(c + 1) & 1]);
           else load_chunk(0, raw[(c + 1) & 1]);              // first chunk of pass 2
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c * 16 + j < NKEY) {
+          for (int j = 0; j < 8; ++j)
+            if (c * 8 + j < NKEY) {
               mx0 = fmaxf(mx0, __uint_as_float(raw[c & 1][0][j]));
               mx1 = fmaxf(mx1, __uint_as_float(raw[c & 1][1][j]));
             }
         }
         const int h0 = grp * 4 + par;
-        const float nshift0 = -fmaf(mx0, sc, s_bmax[h0]), nshift1 = -fmaf(mx1, sc, s_bmax[h0 + 2]);
+        // rows that do not exist (slots beyond the window, windows beyond the level) get p = 2^(-inf) = 0
+        const float nshift0 = valid ? -fmaf(mx0, sc, s_bmax[h0]) : -INFINITY;
+        const float nshift1 = valid ? -fmaf(mx1, sc, s_bmax[h0 + 2]) : -INFINITY;
         // pass 2: p = 2^(s * sc + bias - shift), bf16 pairs along the keys back over the scores
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int bi = (NCH + c) & 1;                      // buffer the chunk was loaded into
+        for (int c = 0; c < NC8; ++c) {
+          const int bi = (NC8 + c) & 1;                      // buffer the chunk was loaded into
           ptx::tmem_ld_wait();
-          if (c + 1 < NCH) load_chunk(c + 1, raw[bi ^ 1]);
-          float pe0[16], pe1[16];
+          if (c + 1 < NC8) load_chunk(c + 1, raw[bi ^ 1]);
+          float pe0[8], pe1[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             pe0[j] = pe1[j] = 0.f;
-            if (c * 16 + j < NKEY) {
-              const uint32_t cd = code[c * 16 + j];
+            if (c * 8 + j < NKEY) {
+              const uint32_t cd = code[c * 8 + j];
               const uint32_t bs = qa_hadd2(qa_hadd2(qa_lds_u32(tx + (cd & 0x3ffu)), qa_lds_u32(ty + ((cd >> 10) & 0x3ffu))),
                                            qa_lds_u32(tz + (cd >> 20)));
               pe0[j] = qa_ex2(qa_fhadd_lo(bs, fmaf(__uint_as_float(raw[bi][0][j]), sc, nshift0)));
               pe1[j] = qa_ex2(qa_fhadd_hi(bs, fmaf(__uint_as_float(raw[bi][1][j]), sc, nshift1)));
             }
           }
-          uint32_t pk0[8], pk1[8];
+          uint32_t pk0[4], pk1[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             l0 += pe0[2 * j] + pe0[2 * j + 1];
             l1 += pe1[2 * j] + pe1[2 * j + 1];
-            pk0[j] = valid ? qa_pack(pe0[2 * j], pe0[2 * j + 1]) : 0u;
-            pk1[j] = valid ? qa_pack(pe1[2 * j], pe1[2 * j + 1]) : 0u;
+            pk0[j] = qa_pack(pe0[2 * j], pe0[2 * j + 1]);
+            pk1[j] = qa_pack(pe1[2 * j], pe1[2 * j + 1]);
           }
-          ptx::tmem_st8(t_u0 + c * 8, pk0);
-          ptx::tmem_st8(t_u1 + c * 8, pk1);
+          ptx::tmem_st4(t_u0 + c * 4, pk0);
+          ptx::tmem_st4(t_u1 + c * 4, pk1);
+        }
+        if (NC8 & 1) {                                       // the PV product reads whole 16-key steps
+          const uint32_t z[4] = {0u, 0u, 0u, 0u};
+          ptx::tmem_st4(t_u0 + NC8 * 4, z);
+          ptx::tmem_st4(t_u1 + NC8 * 4, z);
         }
         lsum[0] = l0;
         lsum[1] = l1;
