@@ -27,6 +27,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float gelu(float v) {
   return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
 }
+// acc_lo += w.lo * a.lo, acc_hi += w.hi * a.hi for packed bf16 pairs: mixed-precision FMA (fp32 accumulate; the
+// bf16 product is exact in fp32, so this equals fmaf on the converted values) -- no unpack instructions
+__device__ __forceinline__ void fma_bf16_pair(float& lo, float& hi, uint32_t w, uint32_t a) {
+  asm("{\n\t.reg .b16 wl, wh, al, ah;\n\tmov.b32 {wl, wh}, %2;\n\tmov.b32 {al, ah}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, wl, al, %0;\n\tfma.rn.f32.bf16 %1, wh, ah, %1;\n\t}"
+      : "+f"(lo), "+f"(hi)
+      : "r"(w), "r"(a));
+}
 __device__ __forceinline__ int64_t hat_row(int64_t t, int K) { return K ? t + t / K + 1 : t; }
 
 template <int V>
@@ -261,11 +269,8 @@ __global__ void __launch_bounds__(256, 4) k_cpe_ln(const CpeParams p) {
           const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a[u]);
           const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wr);
 #pragma unroll
-          for (int j = 0; j < V / 2; ++j) {     // bf16 pair -> two fp32 (exact)
-            acc[2 * j] = fmaf(__uint_as_float(ww[j] << 16), __uint_as_float(aw[j] << 16), acc[2 * j]);
-            acc[2 * j + 1] = fmaf(__uint_as_float(ww[j] & 0xffff0000u), __uint_as_float(aw[j] & 0xffff0000u),
-                                  acc[2 * j + 1]);
-          }
+          for (int j = 0; j < V / 2; ++j)       // bf16 x bf16 + fp32 in one instruction each (FHFMA.BF16, exact product)
+            fma_bf16_pair(acc[2 * j], acc[2 * j + 1], ww[j], aw[j]);
         }
       }
       warp_ln_planar<V>(acc, s_ln, s_ln + C, lane, 1e-5f);
