@@ -129,6 +129,58 @@ __device__ __forceinline__ void ml_res_add(uint32_t stage, int lane, const uint4
   }
 }
 
+// Fast path of epilogue 2 for the block kernel (PJ, contiguous output rows): acc2 already holds
+// s + b2 + fc2(...), so there is no bias and no residual to add and the output row of a tile row is
+// arithmetic (no shuffles).  One call = the 32 accumulator columns from col0 of the warp's lane quadrant.
+// Per 16-column unit the rows go through the warp's transposing stage (lane l then holds 4 consecutive
+// columns of rows (l >> 2) + 8 i: 64 B contiguous per 4 lanes); the four transposed loads of a unit are
+// issued together and its global stores run behind the stage traffic of the next unit.  The stores are the
+// slow part (the SM's write path, ~30 B / clock): the block kernel gives them to warps of their own.
+template <int C>
+__device__ __forceinline__ void ml_epi2_slice(const MlpParams& p, int tile, int quad, int lane, uint32_t lane_base,
+                                              uint32_t stage, int col0, uint32_t arrive_bar) {
+  const int row0 = tile * ML_BM + quad * 32 + (lane >> 2), seg = lane & 3;
+  uint32_t raw[32];
+  ptx::tmem_ld32(lane_base + 256 + col0, raw);
+  ptx::tmem_ld_wait();
+  if (arrive_bar) {                                          // acc2 fully read by this warp
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(arrive_bar);
+  }
+  uint4 a[4];
+  auto flush = [&](int c0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int orr = row0 + 8 * i;
+      if (orr < p.M) {
+        const size_t col = (size_t)(c0 + seg * 4);
+        if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(p.out_f32 + (size_t)orr * C + col) = a[i];
+        if (p.out_bf16 && !(p.dbg & 2)) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(a[i].x), __uint_as_float(a[i].y));
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(a[i].z), __uint_as_float(a[i].w));
+          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)orr * C + col) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    __syncwarp();                                            // the previous unit's transposed loads have completed
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd)
+      ml_sts128(ml_stage_addr(stage, lane, qd), raw[u * 16 + 4 * qd], raw[u * 16 + 4 * qd + 1],
+                raw[u * 16 + 4 * qd + 2], raw[u * 16 + 4 * qd + 3]);
+    if (u == 1) flush(col0);                                 // global stores of unit 0
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = ml_lds128(ml_stage_addr(stage, (lane >> 2) + 8 * i, seg));
+  }
+  flush(col0 + 16);
+  __syncwarp();                                              // the stage is free again
+}
+
 template <int C, bool PJ = false>
 struct MlpSmem {
   static constexpr int KB1 = C / 64;                 // K blocks of GEMM 1
@@ -144,10 +196,11 @@ struct MlpSmem {
   static constexpr int OFF_ST = OFF_W + W_BYTES;
   static constexpr int OFF_B1 = OFF_ST + ST_BYTES;   // b1 [4C] fp32
   static constexpr int OFF_B2 = OFF_B1 + 4 * C * 4;  // b2 [C] fp32
-  static constexpr int OFF_BAR = OFF_B2 + C * 4;
+  static constexpr int OFF_BAR = OFF_B2 + (PJ ? 0 : C * 4);   // PJ: b2 is folded into epilogue 0 (s_pj)
   static constexpr int OFF_PJ = OFF_BAR + 256;       // PJ: proj bias | norm2 gamma | norm2 beta | b2   [4][C] fp32
   static constexpr int OFF_LNX = OFF_PJ + 4 * C * 4; // PJ: LayerNorm statistics exchange [2 halves][128 rows] float2
-  static constexpr int TOTAL = PJ ? OFF_LNX + 2048 : OFF_BAR + 256;
+  static constexpr int OFF_ST2 = OFF_LNX + 2048;     // PJ: transposing stages of the four store warps
+  static constexpr int TOTAL = PJ ? OFF_ST2 + 4 * 2048 : OFF_BAR + 256;
 };
 
 // cycle accounting for CTA 0 (diagnostics; prof == nullptr in production)
@@ -183,6 +236,10 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   const uint32_t c2_full = bar + 200, c2_empty = bar + 208;   // acc2
   const uint32_t s_tmem = bar + 216;
   const uint32_t o_full = bar + 224, c0_full = bar + 232;     // PJ: o tile landed, GEMM 0 done
+  const uint32_t seed_done = bar + 240;                       // PJ split mode: s + b2 moved into acc2
+  // PJ with contiguous output rows (the block kernel): the four otherwise idle warps 9-12 write the finished tile
+  // out (epilogue 2) while warps 0-7 already run epilogue 0 of the next tile
+  const bool split = PJ && !p.out_rows && !(p.dbg & 8);
   float* s_pj = reinterpret_cast<float*>(smem + S::OFF_PJ);   // PJ: bp | gamma | beta | b2
   float2* s_lnx = reinterpret_cast<float2*>(smem + S::OFF_LNX);
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 216);
@@ -197,7 +254,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   const long long t_role = PROF ? clock64() : 0;
 
   for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) s_b1[i] = 0.5f * p.b1[i];   // epilogue 1 works on (acc + b1) / 2
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_b2[i] = PJ ? 0.f : p.b2[i];   // PJ: b2 is folded into epilogue 0
+  if constexpr (!PJ) for (int i = threadIdx.x; i < C; i += blockDim.x) s_b2[i] = p.b2[i];
   if constexpr (PJ) {
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
       s_pj[i] = p.bp[i]; s_pj[C + i] = p.ln_g[i]; s_pj[2 * C + i] = p.ln_b[i]; s_pj[3 * C + i] = p.b2[i];
@@ -211,7 +268,8 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
     ptx::mbar_init(a1_empty, 1);
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(c1_full + 8 * b, 1); ptx::mbar_init(h_full + 8 * b, 8); }
     ptx::mbar_init(c2_full, 1);
-    ptx::mbar_init(c2_empty, 8);
+    ptx::mbar_init(c2_empty, split ? 4 : 8);
+    ptx::mbar_init(seed_done, 8);
     ptx::fence_barrier_init();
   }
   if (warp == 8) { ptx::tmem_alloc(s_tmem, 512); ptx::tmem_relinquish(); }
@@ -284,6 +342,19 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
     }
   } else if (warp >= 9) {
     // ===================== y-tile producers =====================
+    if (split) {
+      // ===================== store warps (block kernel): epilogue 2 of every tile =====================
+      const int q2 = warp & 3;                               // TMEM lane quadrant of this warp (hardware: warp % 4)
+      const uint32_t lb2 = tmem_base + ((uint32_t)(q2 * 32) << 16);
+      const uint32_t st2 = base + S::OFF_ST2 + (uint32_t)(warp - 9) * 2048u;
+      for (int it = 0; it < n_my; ++it) {
+        ptx::mbar_wait_sleep(c2_full, it & 1, 64);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int sl = 0; sl < C / 32; ++sl)
+          ml_epi2_slice<C>(p, blockIdx.x + it * gridDim.x, q2, lane, lb2, st2, sl * 32, sl + 1 == C / 32 ? c2_empty : 0u);
+      }
+    }
     const int pt = (warp - 9) * 32 + lane;
     const int c = pt & 7, rbase = pt >> 3;
     for (int it = 0; it < (PJ ? 0 : n_my); ++it) {       // PJ: the A buffer is filled by TMA (o) and by epilogue 0 (y)
@@ -315,7 +386,8 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       auto gemm1 = [&](int t, int j) {
         const uint32_t q = (uint32_t)t * NCH + j, b = q & 1;
         for (int h = 0; h < G1S; ++h, ++g) {
-          if (j == 0) { ML_T0(); ptx::mbar_wait(a1_full + 8 * (2 * h), t & 1); ptx::mbar_wait(a1_full + 8 * (2 * h + 1), t & 1); ML_ACC(0); }
+          if (j == 0) { ML_T0(); ptx::mbar_wait(a1_full + 8 * (2 * h), t & 1); ptx::mbar_wait(a1_full + 8 * (2 * h + 1), t & 1);
+                        if (split && h == 0) ptx::mbar_wait(seed_done, t & 1); ML_ACC(0); }
           const uint32_t s = g % RING, ph = (g / RING) & 1;
           { ML_T0(); ptx::mbar_wait(w_full + 8 * s, ph); ML_ACC(1); }
           ML_T0();
@@ -449,7 +521,21 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
     };
 
     // epilogue 2: acc2 + b2 + residual -> x (fp32) [+ bf16 shadow], coalesced through the stage
+    // one 32-column slice of this warp's column half of tile t (see ml_epi2_slice)
+    auto epi2_slice = [&](int t, int sl, bool last) {
+      ml_epi2_slice<C>(p, blockIdx.x + t * gridDim.x, quad, lane, lane_base, stage, half * (C / 2) + sl * 32,
+                       last ? c2_empty : 0u);
+    };
+    auto epi2_fast = [&](int t) {
+      { ML_T0(); ptx::mbar_wait(c2_full, t & 1); ML_ACC(10); }
+      ptx::tc_fence_after();
+      ML_T0();
+#pragma unroll 1
+      for (int sl = 0; sl < C / 64; ++sl) epi2_slice(t, sl, sl + 1 == C / 64);
+      ML_ACC(11);
+    };
     auto epi2 = [&](int t) {
+      if (PJ && !p.out_rows && !(p.dbg & 8)) { epi2_fast(t); return; }
       const int tile = blockIdx.x + t * gridDim.x;
       const int m = tile * ML_BM + r;
       int32_t orow = -1;
@@ -482,7 +568,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
           __syncwarp();
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
-            const float4 bb = *reinterpret_cast<const float4*>(s_b2 + cbase + c0 + u * 16 + 4 * qd);
+            const float4 bb = PJ ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(s_b2 + cbase + c0 + u * 16 + 4 * qd);
             ml_sts128(ml_stage_addr(stage, lane, qd), __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd]) + bb.x),
                       __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd + 1]) + bb.y),
                       __float_as_uint(__uint_as_float(raw[u * 16 + 4 * qd + 2]) + bb.z),
@@ -533,8 +619,9 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       const float* v_b2 = s_pj + 3 * C + cbase;
       uint4 rbuf[8];
       ml_res_issue(p.res, orow, C, cbase, lane, rbuf);
-      ptx::mbar_wait(c0_full, t & 1);
+      { ML_T0(); ptx::mbar_wait(c0_full, t & 1); ML_ACC(15); }
       ptx::tc_fence_after();
+      const long long t_e0 = PROF ? clock64() : 0;
       const uint32_t t_src = lane_base + cbase, t_dst = lane_base + 256 + cbase;
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
@@ -562,10 +649,10 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
           for (int e = 0; e < 4; ++e) {
             const float d = v[4 * q + e] - shift;
             s1 += d; s2 = fmaf(d, d, s2);
-            raw[4 * q + e] = __float_as_uint(v[4 * q + e] + bb[e]);
+            raw[4 * q + e] = __float_as_uint(v[4 * q + e] + (split ? 0.f : bb[e]));
           }
         }
-        ptx::tmem_st32(t_dst + c0, raw);
+        ptx::tmem_st32((split ? t_src : t_dst) + c0, raw);
       }
       // per-half (mean, M2) -> exchange with the warp that owns the other column half of this row
       const float nh = (float)CW;
@@ -582,14 +669,15 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
         uint32_t raw[32];
-        ptx::tmem_ld32(t_dst + c0, raw);
+        ptx::tmem_ld32((split ? t_src : t_dst) + c0, raw);
         ptx::tmem_ld_wait();
         uint32_t w[16];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 gm = *reinterpret_cast<const float4*>(v_g + c0 + 4 * q);
           const float4 bt = *reinterpret_cast<const float4*>(v_be + c0 + 4 * q);
-          const float4 b2 = *reinterpret_cast<const float4*>(v_b2 + c0 + 4 * q);
+          float4 b2 = *reinterpret_cast<const float4*>(v_b2 + c0 + 4 * q);
+          if (split) b2 = make_float4(0.f, 0.f, 0.f, 0.f);
           const float y0 = (__uint_as_float(raw[4 * q]) - b2.x - mean) * rstd * gm.x + bt.x;
           const float y1 = (__uint_as_float(raw[4 * q + 1]) - b2.y - mean) * rstd * gm.y + bt.y;
           const float y2 = (__uint_as_float(raw[4 * q + 2]) - b2.z - mean) * rstd * gm.z + bt.z;
@@ -613,6 +701,32 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       }
       // the exchange slot is rewritten only after both halves passed this barrier
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      if (split) {
+        // seed of GEMM 2: s + b2 from the GEMM-0 columns into acc2, as soon as the store warps have read the
+        // previous tile out of it; GEMM 1 of chunk 0 (which overwrites these columns) waits for seed_done
+        if (t > 0) { ML_T0(); ptx::mbar_wait(c2_empty, (t & 1) ^ 1); ML_ACC(3); }
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < CW; c0 += 32) {
+          uint32_t raw[32];
+          ptx::tmem_ld32(t_src + c0, raw);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(v_b2 + c0 + 4 * q);
+            raw[4 * q] = __float_as_uint(__uint_as_float(raw[4 * q]) + b.x);
+            raw[4 * q + 1] = __float_as_uint(__uint_as_float(raw[4 * q + 1]) + b.y);
+            raw[4 * q + 2] = __float_as_uint(__uint_as_float(raw[4 * q + 2]) + b.z);
+            raw[4 * q + 3] = __float_as_uint(__uint_as_float(raw[4 * q + 3]) + b.w);
+          }
+          ptx::tmem_st32(t_dst + c0, raw);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(seed_done);
+      }
+      if (PROF) lacc[18] += clock64() - t_e0;
     };
 
     // static schedule: the final tile of iteration t - 1 is written out between the first two
@@ -629,7 +743,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
         }
       }
       if constexpr (PJ) {
-        if (it > 0) epi2(it - 1);
+        if (it > 0 && !split) epi2(it - 1);                  // split: the store warps write the tiles out
         epi0(it);
         for (int j = 0; j < NCH; ++j) epi1(it, j);
       } else {
@@ -638,15 +752,15 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
         for (int j = 1; j < NCH; ++j) epi1(it, j);
       }
     }
-    if (n_my > 0) epi2(n_my - 1);
+    if (n_my > 0 && !split) epi2(n_my - 1);
     if (PROF) lacc[12] = clock64() - t_role;
   }
   if (PROF && blockIdx.x == 0) {
     auto dump = [&](int a, int b) { for (int i = a; i < b; ++i) p.prof[i] = lacc[i]; };
     if (threadIdx.x == 8 * 32) dump(0, 8);
-    if (threadIdx.x == 0) { dump(8, 13); dump(17, 23); }
+    if (threadIdx.x == 0) { dump(8, 13); dump(17, 23); if (PJ) dump(15, 16); }
     if (threadIdx.x == 13 * 32) dump(13, 15);
-    if (threadIdx.x == 9 * 32) dump(15, 17);
+    if (threadIdx.x == 9 * 32 && !PJ) dump(15, 17);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -725,20 +839,21 @@ static int mlp_dispatch(const void* A, const void* Wp, const float* bp, const fl
   if (want_prof && !prof) cudaMalloc(&prof, 32 * sizeof(long long));
   if (want_prof) cudaMemsetAsync(prof, 0, 32 * sizeof(long long), st);
   MlpParams p{(const __nv_bfloat16*)A, (int)M, b1, b2, res, out_f32, (__nv_bfloat16*)out_bf16, out_rows,
-              dbg, (want_prof && !pj) ? prof : nullptr, bp, ln_g, ln_b, 1e-5f};
+              dbg, want_prof ? prof : nullptr, bp, ln_g, ln_b, 1e-5f};
   int rc;
-  if (pj) rc = C == 128 ? launch_mlp<128, false, true>(t1, t2, to, tp, p, st) : launch_mlp<256, false, true>(t1, t2, to, tp, p, st);
+  if (pj && want_prof && C == 256) rc = launch_mlp<256, true, true>(t1, t2, to, tp, p, st);
+  else if (pj) rc = C == 128 ? launch_mlp<128, false, true>(t1, t2, to, tp, p, st) : launch_mlp<256, false, true>(t1, t2, to, tp, p, st);
   else if (want_prof) rc = C == 128 ? launch_mlp<128, true, false>(t1, t2, to, tp, p, st) : launch_mlp<256, true, false>(t1, t2, to, tp, p, st);
   else rc = C == 128 ? launch_mlp<128, false, false>(t1, t2, to, tp, p, st) : launch_mlp<256, false, false>(t1, t2, to, tp, p, st);
-  if (want_prof && !pj && rc == HFL_OK) {
+  if (want_prof && (!pj || C == 256) && rc == HFL_OK) {
     long long h[32];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
     static const char* nm[] = {"mma:a1_full", "mma:w_full(g1)", "mma:h_full", "mma:c2_empty", "mma:w_full(g2)",
                                "mma:issue(g1)", "mma:issue(g2)", "mma:total", "epi:c1_full", "epi:e1_work",
                                "epi:c2_full", "epi:e2_work", "epi:total", "tma:w_empty", "tma:total",
-                               "y:a1_empty", "y:total", "e2:tmem_ld", "e2:(unused)", "e2:transpose+stores", "e1:tmem_ld", "e1:gelu", "e1:tmem_st"};
-    fprintf(stderr, "[hfl_mlp_fused prof C=%d M=%lld]", C, (long long)M);
+                               "y:a1_empty|e0:c0_full", "y:total", "e2:tmem_ld", "e0:work", "e2:transpose+stores", "e1:tmem_ld", "e1:gelu", "e1:tmem_st"};
+    fprintf(stderr, "[hfl_%smlp_fused prof C=%d M=%lld tiles/CTA=%.1f]", pj ? "proj_" : "", C, (long long)M, (double)((M + 127) / 128) / sm_count());
     for (int i = 0; i < 23; ++i) fprintf(stderr, " %s=%.1fk", nm[i], h[i] / 1e3);
     fprintf(stderr, "\n");
   }
