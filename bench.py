@@ -228,6 +228,8 @@ def run_native(args, rank, world, device):
         o = ahead.pop(('e', i), None) or build_batch(batches[i % n_pool], depth, 2, device)
         ahead[('e', i + 1)] = build_batch(batches[(i + 1) % n_pool], depth, 2, device)
         d = model({'octree': o})['global']
+        if world > 1:
+            d = gather(d)[rank]                      # the descriptor all-gather is part of the end-to-end step
         k = i & 1
         consume(k)                                   # result of step i - 2
         res_pin[k].copy_(d, non_blocking=True)
@@ -362,30 +364,69 @@ def emit(obj):
 
 
 def cpu_baseline(args, sample=4, steps=1, warmup=0):
-    """The oracle (CPU port of the reference path: per-submap octree build, merge,
-    neighbour construction, fp32 forward) on a bounded sample of the same workload."""
-    from oracle import model_ref as M, octree_ref as R
+    """The reference's CPU implementation of the path on a bounded sample of the same workload, in the three
+    phases of BASELINE.md section 3: per-submap octree build loop, merge_octrees + construct_all_neigh, model
+    forward.  kind = "reference": the reference's OWN, unmodified models/*.py + model_factory staged under
+    oracle/_ref (oracle/build_ref.py), run over the ocnn stand-ins of oracle/ocnn_standin.py (ocnn 2.2.2 and the
+    CUDA-only dwconv extension cannot be installed offline).  kind = "port" (oracle/model_ref.py) only when
+    oracle/_ref has not been staged."""
+    from oracle import build_ref
     from hotformerloc_b200.config.presets import write_configs, TRAIN_PRESETS
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    depth = TRAIN_PRESETS[args.config]['octree_depth']
     d = tempfile.mkdtemp(prefix='hfl_cfg_')
     paths = write_configs(d, args.config, dataset_folder=d)
-    hp = M.HParams.from_cfg(paths['model_config'])
-    depth = TRAIN_PRESETS[args.config]['octree_depth']
-    shapes = json.load(open(os.path.join(ROOT, 'tests', 'golden', f'state_shapes_{args.config}.json')))
-    sd = M.synthetic_state_dict(shapes, mode='init')
+    phases = {'octree_build_loop': [], 'merge_and_neigh': [], 'forward': []}
+    if build_ref.available():
+        from oracle import ocnn_standin as S
+        S.install(build_ref.DST)
+        torch.manual_seed(0)
+        model = S.reference_model(paths['model_config'])
+        kind = 'reference'
+
+        def one(clouds):
+            t0 = time.perf_counter()
+            octs = []
+            for c in clouds:                                   # eval/pnv_evaluate.py:173-176
+                o = S.Octree(depth, 2)
+                o.build_octree(S.Points(torch.as_tensor(c)))
+                octs.append(o)
+            t1 = time.perf_counter()
+            mo = S.merge_octrees(octs)                         # eval/pnv_evaluate.py:122-126
+            mo.construct_all_neigh()
+            t2 = time.perf_counter()
+            with torch.inference_mode():
+                model({'octree': mo})['global']
+            t3 = time.perf_counter()
+            return t1 - t0, t2 - t1, t3 - t2
+    else:
+        from oracle import model_ref as M, octree_ref as R
+        hp = M.HParams.from_cfg(paths['model_config'])
+        shapes = json.load(open(os.path.join(ROOT, 'tests', 'golden', f'state_shapes_{args.config}.json')))
+        sd = M.synthetic_state_dict(shapes, mode='init')
+        kind = 'port'
+
+        def one(clouds):
+            t0 = time.perf_counter()
+            o = R.build_batch(clouds, depth)                   # build + merge + neighbours in one call
+            t1 = time.perf_counter()
+            M.forward(sd, o, hp)
+            t2 = time.perf_counter()
+            return t1 - t0, 0.0, t2 - t1
     times = []
     for i in range(warmup + steps):
         clouds = synthetic_batches(1, sample, args.points, seed0=5000 + i)[0]
-        t = time.perf_counter()
-        o = R.build_batch(clouds, depth)
-        M.forward(sd, o, hp)
+        ph = one(clouds)
         if i >= warmup:
-            times.append(time.perf_counter() - t)
+            times.append(sum(ph))
+            for k, v in zip(phases, ph):
+                phases[k].append(v)
     sec = float(np.mean(times))
-    return {'value': sample / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+    return {'value': sample / sec, 'unit': UNIT, 'cores': cores, 'kind': kind,
             'sample': f'{sample} submaps of {args.points} points per step, {steps} step(s), '
-                      f'fp32, torch threads = {cores}', 'seconds_per_step': sec}
+                      f'fp32, torch threads = {cores}', 'seconds_per_step': sec,
+            'phase_seconds_per_step': {k: float(np.mean(v)) for k, v in phases.items()}}
 
 
 def run_reference(args, rank, world):
@@ -399,7 +440,7 @@ def run_reference(args, rank, world):
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
            'config': {'workload': f'{args.config} cfg, {args.batch} synthetic {args.points}-point submaps per step per GPU, '
                                   f'random-init weights (BASELINE.json configs[1])',
-                      'sample': f'each step = {sample} submaps of that workload on the host cores'},
+                      'sample': f'each step = {sample} submaps of that workload on the host cores ({cpu["kind"]}: see cpu_baseline)'},
            'cpu_baseline': cpu,
            'e2e': {'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
                    'd2h_bytes_per_step': 0}}
@@ -415,7 +456,7 @@ def main():
     ap.add_argument('--config', default='oxford')
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--points', type=int, default=4096)
-    ap.add_argument('--cpu-sample', type=int, default=8)
+    ap.add_argument('--cpu-sample', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop and exit '

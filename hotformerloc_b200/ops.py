@@ -139,8 +139,10 @@ def knn_topk(q: torch.Tensor, db: torch.Tensor, k: int = 25, idx_offset: int = 0
     nq, dim = q.shape
     od = torch.empty((nq, k), dtype=torch.float32, device=q.device)
     oi = torch.empty((nq, k), dtype=torch.int32, device=q.device)
-    N.check(N.lib().hfl_knn_topk(_p(q.contiguous()), nq, _p(db.contiguous()), db.shape[0], dim, k,
-                                 idx_offset, _p(od), _p(oi), _s()))
+    nb = int(N.lib().hfl_knn_workspace_bytes(nq, db.shape[0], k))
+    ws = torch.empty((max(nb, 8),), dtype=torch.uint8, device=q.device)
+    N.check(N.lib().hfl_knn_topk_ws(_p(q.contiguous()), nq, _p(db.contiguous()), db.shape[0], dim, k,
+                                    idx_offset, _p(od), _p(oi), _p(ws), nb, _s()))
     return od, oi
 
 

@@ -213,6 +213,11 @@ int hfl_gem_head(const float* pooled, int32_t B, int32_t in_dim, const float* w,
  * merge of all-gathered partial lists. */
 int hfl_knn_topk(const float* q, int32_t nq, const float* db, int32_t ndb, int32_t dim, int32_t k,
                  int32_t idx_offset, float* out_d, int32_t* out_i, void* stream);
+/* Same with a caller-owned workspace of hfl_knn_workspace_bytes(): the database shard is split over the grid
+ * (sorted partial lists per split, folded by the merge kernel) so that small query sets fill the GPU too. */
+int64_t hfl_knn_workspace_bytes(int32_t nq, int32_t ndb, int32_t k);
+int hfl_knn_topk_ws(const float* q, int32_t nq, const float* db, int32_t ndb, int32_t dim, int32_t k,
+                    int32_t idx_offset, float* out_d, int32_t* out_i, void* ws, int64_t ws_bytes, void* stream);
 int hfl_topk_merge(const float* in_d, const int32_t* in_i, int32_t parts, int32_t nq, int32_t k,
                    float* out_d, int32_t* out_i, void* stream);
 

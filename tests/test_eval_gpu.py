@@ -97,3 +97,49 @@ def test_evaluate_end_to_end_vs_oracle(tmp_path):
     assert abs(st['average']['average']['ave_one_percent_recall'] - stats['average']['ave_one_percent_recall']) < 1e-9
     S.pnv_write_eval_stats(os.path.join(root, 'res_splits.txt'), 'prefix', st)
     assert 'Split: [' in open(os.path.join(root, 'res_splits.txt')).read()
+
+
+def test_config4_recall_vs_oracle_golden(tmp_path):
+    """BASELINE.json configs[3] on the 4 x 512 subset SURVEY.md section 8d names: Wild-Places cfg (cylindrical
+    coordinates, K = 48, val_batch_size 128), 4 traversals x 512 places x 30 k points written in the reference's
+    on-disk format (.pcd + evaluation dicts), embedded through get_latent_vectors and ranked through get_recall.
+    Golden = tests/golden/config4_recall.npz: the REFERENCE'S own loaders / Normalize / CylindricalCoordinates /
+    get_recall around the fp32 CPU oracle forward (oracle/make_golden_config4.py, 2048 submaps on the CPU).
+    Bars: descriptors cosine >= 0.999; recall@1, recall@1 % and MRR within 0.5 pt of the oracle's (bf16 descriptors
+    may swap a handful of near-tied candidates among 512; BASELINE.json north_star asks for 0.1 pt on REAL data,
+    where positives are not near-ties)."""
+    import json
+    from hotformerloc_b200.config.presets import write_configs
+    from hotformerloc_b200.datasets.synthetic import make_eval_dataset
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    from hotformerloc_b200.misc.utils import TrainingParams
+    from hotformerloc_b200.models.model_factory import model_factory
+    gold = np.load(os.path.join(GOLDEN, 'config4_recall.npz'))
+    runs, per_run, points = int(gold['runs']), int(gold['per_run']), int(gold['points'])
+    root = str(tmp_path)
+    sets = make_eval_dataset(root, runs, per_run, points, seed=11)
+    paths = write_configs(os.path.join(root, 'cfg'), 'wild-places', dataset_folder=root)
+    params = TrainingParams(paths['config'], paths['model_config'])
+    assert params.val_batch_size == 128 and params.model_params.coordinates == 'cylindrical'
+    shapes = json.load(open(os.path.join(GOLDEN, 'state_shapes_wild-places.json')))
+    model = model_factory(params.model_params)
+    model.load_state_dict(M.synthetic_state_dict(shapes, mode='init'))
+    model = model.cuda().eval()
+    emb = [E.get_latent_vectors(model, s, 'cuda', params) for s in sets]
+    for r in range(runs):
+        assert emb[r].shape == (per_run, 256)
+        keep = gold[f'desc_run{r}']
+        assert cosine(emb[r][:len(keep)], keep).min() >= 0.999, r
+    recs, oprs, mrrs = [], [], []
+    for m in range(runs):
+        for n in range(runs):
+            if m == n and params.skip_same_run:
+                continue
+            rec, opr, mrr = E.get_recall(m, n, emb, emb, sets, sets)
+            assert abs(rec[0] - gold[f'recall_{m}_{n}'][0]) < 1.0, (m, n, rec[0], gold[f'recall_{m}_{n}'][0])
+            recs.append(rec), oprs.append(opr), mrrs.append(mrr)
+    ave = np.mean(recs, axis=0)
+    assert abs(ave[0] - gold['ave_recall'][0]) < 0.5, (ave[0], gold['ave_recall'][0])
+    assert np.abs(ave - gold['ave_recall']).max() < 0.5
+    assert abs(np.mean(oprs) - gold['ave_one_percent_recall']) < 0.5
+    assert abs(np.mean(mrrs) - gold['ave_mrr']) < 0.5

@@ -348,6 +348,39 @@ def test_knn_matches_bruteforce():
     assert torch.equal(mi, i) and torch.equal(md, d)
 
 
+def test_knn_full_size_with_ties_and_small_query_sets():
+    """BASELINE.json configs[3] size (8192 x 8192 x 256) incl. exact duplicates in the database (index ties must
+    resolve to the lower index, as a stable sort of the reference's distances does), a query set smaller than one
+    tile, a database smaller than k, and the split / unsplit paths agreeing bit for bit."""
+    torch.manual_seed(11)
+    db = F.normalize(torch.randn(8192, 256), dim=1)
+    db[4096:4096 + 512] = db[:512]                       # duplicates: distance ties at different indices
+    db = db.to(DEV)
+    q = F.normalize(db[torch.randperm(8192)[:8192].to(DEV)] + 0.05 * torch.randn(8192, 256, device=DEV), dim=1)
+    d, i = _ops().knn_topk(q, db, 25)
+    ref = torch.cdist(q.double(), db.double()) ** 2
+    rd, _ = ref.topk(25, dim=1, largest=False)
+    assert torch.allclose(d.double(), rd, atol=2e-5)
+    true_d = ref.gather(1, i.long())
+    assert bool((true_d <= rd[:, -1:] + 1e-6).all())
+    assert bool((d[:, 1:] >= d[:, :-1]).all())
+    same = d[:, 1:] == d[:, :-1]
+    assert bool((i[:, 1:][same] > i[:, :-1][same]).all())  # ties ordered by index
+    assert all(len(set(r.tolist())) == 25 for r in i[:64].cpu())
+    # unsplit path (no workspace) gives the identical lists
+    from hotformerloc_b200 import native as N
+    od = torch.empty_like(d); oi = torch.empty_like(i)
+    N.check(N.lib().hfl_knn_topk(q.data_ptr(), 8192, db.data_ptr(), 8192, 256, 25, 0, od.data_ptr(), oi.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(od, d) and torch.equal(oi, i)
+    # 5 queries (one partial tile, many database splits) and a database smaller than k
+    d5, i5 = _ops().knn_topk(q[:5], db, 25)
+    assert torch.equal(d5, d[:5]) and torch.equal(i5, i[:5])
+    d3, i3 = _ops().knn_topk(q[:70], db[:10], 25)
+    assert bool((i3[:, 10:] == -1).all()) and bool(torch.isinf(d3[:, 10:]).all())
+    assert torch.equal(i3[:, :10].long().sort(1).values, torch.arange(10, device=DEV).expand(70, 10))
+
+
 # ---------------------------------------------------------------------------
 # relay-token / pooling-head kernels in isolation
 # ---------------------------------------------------------------------------

@@ -45,3 +45,22 @@ def test_oracle_reproduces_reference_descriptors(golden_dir, name, tmp_path):
     assert np.abs(g - ref).max() < 1e-5
     cos = (g * ref).sum(1) / np.linalg.norm(g, axis=1) / np.linalg.norm(ref, axis=1)
     assert cos.min() > 0.99999
+
+
+def test_staged_reference_reproduces_golden(golden_dir):
+    """oracle/_ref (the reference's own models/*.py staged by oracle/build_ref.py -- the `--impl reference` arm and
+    the cpu_baseline of bench.py) gives the frozen reference descriptors again: the staged copy is the code the
+    goldens came from.  Skipped where it has not been staged (it is a build output, not part of the history)."""
+    from oracle import build_ref, ocnn_standin as S
+    if not build_ref.available():
+        pytest.skip('oracle/_ref not staged (python -m oracle.build_ref needs /root/reference)')
+    name = 'oxford_b1_init'
+    cfg, depth, spec, seed, mode = CASES[name]
+    S.install(build_ref.DST)
+    m = S.reference_model(os.path.join(build_ref.DST, 'models', f'hotformerloc_{cfg}_cfg.txt'))
+    shapes = json.load(open(os.path.join(golden_dir, f'state_shapes_{cfg}.json')))
+    m.load_state_dict(M.synthetic_state_dict(shapes, mode=mode))
+    with torch.inference_mode():
+        y = m(S.make_batch(_clouds(name), depth))['global'].numpy()
+    ref = np.load(os.path.join(golden_dir, 'descriptors.npz'))[name + '_reference']
+    assert np.abs(y - ref).max() < 1e-6
