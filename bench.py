@@ -447,6 +447,29 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+def run_eval_workload(args, rank, world):
+    """BASELINE.json configs[3] as a bench line: Wild-Places cfg, `--eval-runs` traversals x `--eval-per-run`
+    submaps of ~30 k points in the reference's on-disk format -> loaders -> Normalize / cylindrical -> device
+    octrees -> descriptors (batches sharded over the ranks) -> all-gather -> database-sharded top-25 -> merge ->
+    recall.  One step = the whole evaluation (files already written); time = wall clock around embed + search,
+    max over ranks through the barriers inside (tools/config4_eval.py)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import config4_eval
+    r = config4_eval.main(['--runs', str(args.eval_runs), '--per-run', str(args.eval_per_run), '--points', '30000',
+                           '--out', os.path.join(ROOT, 'gpurun_out', f'config4_{world}gpu.json')], emit=False)
+    if rank != 0:
+        return
+    sec = r['embed_seconds_incl_file_io_and_host_prep'] + r['search_seconds']
+    emit({'metric': 'submaps_per_sec_eval_files_to_recall', 'value': r['submaps'] / sec, 'unit': UNIT, 'n_gpus': world,
+          'steps': 1, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+          'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+          'config': {'workload': r['config'] + ' (BASELINE.json configs[3])', 'parallelism': f'batch-sharded x{world}, '
+                     'database-sharded top-k'},
+          'recall': {k: r[k] for k in ('recall_at_1', 'recall_at_5', 'recall_at_1pct', 'mrr')},
+          'embed_seconds': r['embed_seconds_incl_file_io_and_host_prep'], 'search_seconds': r['search_seconds'],
+          'checks': r['checks']})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -458,6 +481,10 @@ def main():
     ap.add_argument('--points', type=int, default=4096)
     ap.add_argument('--cpu-sample', type=int, default=4)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='embed', choices=['embed', 'eval'],
+                    help='embed = the headline step (default); eval = BASELINE.json configs[3], files -> recall')
+    ap.add_argument('--eval-runs', type=int, default=4)
+    ap.add_argument('--eval-per-run', type=int, default=8192)
     ap.add_argument('--ncu-step', action='store_true',
                     help='profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop and exit '
                          '(use with ncu --profile-from-start off); prints no bench line')
@@ -483,7 +510,10 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
     try:
-        run_native(args, rank, world, device)
+        if args.workload == 'eval':
+            run_eval_workload(args, rank, world)
+        else:
+            run_native(args, rank, world, device)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -37,17 +37,18 @@ import torch.distributed as dist
 from hotformerloc_b200.datasets.synthetic import make_eval_dataset as make_dataset  # noqa: E402
 
 
-def main():
+def main(argv=None, emit=True):
     ap = argparse.ArgumentParser()
     ap.add_argument('--runs', type=int, default=4)
     ap.add_argument('--per-run', type=int, default=256)
     ap.add_argument('--points', type=int, default=30000)
     ap.add_argument('--root', default='/tmp/hfl_config4')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'config4.json'))
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
     torch.cuda.set_device(local)
-    if world > 1:
+    own_pg = world > 1 and not dist.is_initialized()
+    if own_pg:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from hotformerloc_b200 import ops
     from hotformerloc_b200.config.presets import write_configs
@@ -87,6 +88,7 @@ def main():
             mrrs.append(mrr)
     torch.cuda.synchronize()
     t_search = time.time() - t0
+    out = None
     checks = {}
     if rank == 0:
         # (1) sharded descriptors == one-GPU descriptors with the reference's batch composition
@@ -121,12 +123,15 @@ def main():
                'embed_submaps_per_s_incl_file_io': round(n_sub / t_embed, 1),
                'search_seconds': round(t_search, 3), 'dataset_write_seconds': round(t_gen, 1),
                'checks': checks}
-        print(json.dumps(out))
+        if emit:
+            print(json.dumps(out))
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         json.dump(out, open(args.out, 'w'), indent=1)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if own_pg:
+            dist.destroy_process_group()
+    return out if rank == 0 else None
 
 
 if __name__ == '__main__':
