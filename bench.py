@@ -321,10 +321,11 @@ def run_native(args, rank, world, device):
     dom = max((k for k in fam if k != 'octree_build'), key=lambda k: fam[k]['ms'])
     roof = roof_of(dom)
     try:        # DRAM bytes of this family's largest launch from the committed ncu --set full capture
-        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json'))).get(dom)
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json'))).get(dom)
         if cap:
             roof['traffic'] = cap['dram_bytes']
-            roof['traffic_source'] = f"profiles/r01_traffic.json: {cap['kernel']}, one launch under ncu"
+            roof['traffic_source'] = (f"profiles/r02_traffic.json: {cap['kernel']}, the family's largest launch "
+                                      f"({cap['ms']:.3f} ms) under ncu --set full")
     except Exception:
         pass
     roof_all = {k: {kk: (round(v, 4) if isinstance(v, float) else v) for kk, v in roof_of(k).items()
