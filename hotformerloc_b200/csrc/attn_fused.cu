@@ -368,11 +368,8 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     const int yw = r >> 6;                                 // drain view of the lane: row r of the y tile
     // +bias, bf16, UMMA operand layouts for one 16-column unit of the QKV chunk of group `grp` (u / 4 =
     // q | k | v, u % 4 = head hl of the group).  Here lane r is row r of the y tile (window yw, slot sl).
-    auto drain_unit = [&](int grp, int sect, int hl) {
+    auto drain_unit = [&](int grp, int sect, int hl, const uint32_t (&raw)[16]) {
       const int dpar = hl & 1, dhp = hl >> 1, u = sect * 4 + hl;
-      uint32_t raw[16];
-      ptx::tmem_ld16(lane_base + T_CHUNK + u * 16, raw);
-      ptx::tmem_ld_wait();
       const float* bg = s_bias + grp * QA_GN + u * 16;
       float v[16];
 #pragma unroll
@@ -411,8 +408,15 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     auto drain_qk = [&](int gi) {
       const long long t_d = PROF ? clock64() : 0;
       const int grp = gi % G;
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) drain_unit(grp, i >> 1, team * 2 + (i & 1));
+      // the next unit's tensor-memory load is in flight while the current one is converted and stored
+      uint32_t raw[2][16];
+      ptx::tmem_ld16(lane_base + T_CHUNK + (team * 2) * 16, raw[0]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ptx::tmem_ld_wait();
+        if (i + 1 < 4) ptx::tmem_ld16(lane_base + T_CHUNK + (((i + 1) >> 1) * 4 + team * 2 + ((i + 1) & 1)) * 16, raw[(i + 1) & 1]);
+        drain_unit(grp, i >> 1, team * 2 + (i & 1), raw[i & 1]);
+      }
       ptx::fence_proxy_async();                            // generic-proxy stores -> UMMA (async proxy)
       ptx::tc_fence_before();
       __syncwarp();
@@ -422,8 +426,12 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     auto drain_v = [&](int gi) {
       const long long t_d = PROF ? clock64() : 0;
       const int grp = gi % G;
-#pragma unroll 1
-      for (int i = 0; i < 2; ++i) drain_unit(grp, 2, team * 2 + i);
+      uint32_t raw[2][16];
+      ptx::tmem_ld16(lane_base + T_CHUNK + (2 * 4 + team * 2) * 16, raw[0]);
+      ptx::tmem_ld16(lane_base + T_CHUNK + (2 * 4 + team * 2 + 1) * 16, raw[1]);
+      ptx::tmem_ld_wait();
+      drain_unit(grp, 2, team * 2, raw[0]);
+      drain_unit(grp, 2, team * 2 + 1, raw[1]);
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
