@@ -35,15 +35,16 @@ def write_pcd(path: str, xyz: np.ndarray) -> None:
         f.write(np.ascontiguousarray(xyz, dtype=np.float32).tobytes())
 
 
-def trajectory_clouds(runs: int, per_run: int, points: int, seed: int = 11, jitter: float = 0.01,
-                      yaw: float = 0.002, drop: float = 0.02) -> List[List[np.ndarray]]:
+def iter_trajectory_clouds(runs: int, per_run: int, points: int, seed: int = 11, jitter: float = 0.01,
+                           yaw: float = 0.002, drop: float = 0.02):
     """``runs`` traversals of one trajectory of ``per_run`` places, in metres (~60 m submaps).  A place is
     a tilted ground plane + 12 box-shaped structures; a traversal re-observes it with point jitter (metres),
     a small yaw (radians) and a fraction of the points dropped -- near-duplicate positives, so recall on
     random-init descriptors is a meaningful check.  Defaults (1 cm, 2 mrad, 2 %) were chosen with the CPU
     oracle: a random-init network is not invariant to larger re-observation noise (5 cm / 30 mrad / 10 %
     gives recall@1 of 5-9 %, i.e. rank order dominated by noise; these give ~100 % with a top-1 margin
-    two orders of magnitude above the bf16 descriptor error).  Returns clouds[run][place] float64 (n, 3)."""
+    two orders of magnitude above the bf16 descriptor error).  Yields (run, place, float64 (n, 3)) in the order
+    the generator draws them (places first, then run by run), one cloud at a time."""
     rng = np.random.default_rng(seed)
 
     def place():
@@ -59,16 +60,20 @@ def trajectory_clouds(runs: int, per_run: int, points: int, seed: int = 11, jitt
         pts = np.concatenate([np.concatenate([xy_g, xy_o]), np.concatenate([z_g, z_o])[:, None]], 1)
         return np.clip(pts, -1, 1) * 30.0
     places = [place() for _ in range(per_run)]
-    out = []
-    for _ in range(runs):
-        run = []
-        for base in places:
+    for r in range(runs):
+        for i, base in enumerate(places):
             ang = rng.normal(0, yaw)
             c, sn = np.cos(ang), np.sin(ang)
             keep = rng.random(len(base)) > drop
             pts = base[keep] + rng.normal(0, jitter, (int(keep.sum()), 3))
-            run.append(pts @ np.array([[c, -sn, 0], [sn, c, 0], [0, 0, 1]]).T)
-        out.append(run)
+            yield r, i, pts @ np.array([[c, -sn, 0], [sn, c, 0], [0, 0, 1]]).T
+
+
+def trajectory_clouds(runs: int, per_run: int, points: int, seed: int = 11, **kw) -> List[List[np.ndarray]]:
+    """All clouds of iter_trajectory_clouds() at once: clouds[run][place] float64 (n, 3)."""
+    out = [[None] * per_run for _ in range(runs)]
+    for r, i, pts in iter_trajectory_clouds(runs, per_run, points, seed, **kw):
+        out[r][i] = pts
     return out
 
 
@@ -90,12 +95,11 @@ def eval_sets(runs: int, per_run: int, subdir: str = 'Venman', ext: str = 'pcd')
 def make_eval_dataset(root: str, runs: int, per_run: int, points: int, seed: int = 11,
                       subdir: str = 'Venman') -> List[Dict]:
     """Write trajectory_clouds() as binary .pcd files under ``root`` and return the evaluation dicts."""
-    clouds = trajectory_clouds(runs, per_run, points, seed)
     sets = eval_sets(runs, per_run, subdir)
     for r in range(runs):
         os.makedirs(os.path.join(root, subdir, f'run{r}', 'Clouds'), exist_ok=True)
-        for i in range(per_run):
-            write_pcd(os.path.join(root, sets[r][i]['query']), clouds[r][i])
+    for r, i, pts in iter_trajectory_clouds(runs, per_run, points, seed):      # written as drawn: one cloud in memory
+        write_pcd(os.path.join(root, sets[r][i]['query']), pts)
     return sets
 
 
