@@ -103,6 +103,47 @@ def prepare_cloud(data: np.ndarray, params: TrainingParams, normalize=None, cyl=
     return data.numpy()
 
 
+def prepare_batch(raws: List[np.ndarray], params: TrainingParams, normalize=None, cyl=None) -> List[np.ndarray]:
+    """prepare_cloud() for the submaps of one evaluation batch at once: the same torch operations, applied to the
+    concatenated points with per-submap scalars broadcast through a segment index, so that the Python / dispatch
+    cost is paid per batch instead of per submap (the per-submap form costs tens of ms of host time per cloud and
+    bounds the file -> descriptor pipeline at a fraction of what the GPU embeds).  Every operation is elementwise
+    or a per-row / per-submap min / max, so the values are bit-identical to the per-submap path
+    (tests/test_host_cpu.py::test_prepare_batch_is_bit_identical); unit-sphere normalisation (a per-submap float
+    mean / max of norms) keeps the per-submap path."""
+    if not raws:
+        return []
+    if normalize is not None and normalize.unit_sphere_norm:
+        return [prepare_cloud(r, params, normalize, cyl) for r in raws]
+    B = len(raws)
+    lens = torch.tensor([len(r) for r in raws], dtype=torch.int64)
+    data = torch.tensor(np.concatenate(raws, axis=0))
+    seg = torch.repeat_interleave(torch.arange(B), lens)
+    if normalize is not None:
+        lo = torch.segment_reduce(data, 'min', lengths=lens, axis=0)
+        hi = torch.segment_reduce(data, 'max', lengths=lens, axis=0)
+        if normalize.zero_mean:
+            data = data - ((lo + hi) * 0.5)[seg]
+        if normalize.scale_factor is not None:
+            data = data / normalize.scale_factor
+        else:
+            box = (hi - lo).max(dim=1).values + 1.0e-6
+            data = data * (2.0 * normalize.norm_range / box)[seg][:, None]
+    keep = torch.all(abs(data) <= 1.0, dim=1)
+    data, seg = data[keep], seg[keep]
+    if cyl is not None:
+        keep = torch.linalg.norm(data[:, :2], dim=1) <= 1.0
+        data, seg = data[keep], seg[keep]
+        data = cyl(data)
+    counts = torch.bincount(seg, minlength=B).tolist()
+    out, o = [], 0
+    arr = data.numpy()
+    for c in counts:
+        out.append(arr[o:o + c])
+        o += c
+    return out
+
+
 def collate_batch(data: List[np.ndarray], device, params: TrainingParams):
     """One merged, neighbour-complete, device-resident octree for a list of prepared clouds."""
     return {'octree': build_batch(data, params.octree_depth, 2, device)}
@@ -177,35 +218,42 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
     spans = shard_batches(len(keys), params.val_batch_size, rank, world)
     chunks = []
 
-    def load(k):
-        return prepare_cloud(pc_loader(os.path.join(params.dataset_folder, data_set[k]['query'])),
-                             params, normalize, cyl)
+    def read(k):
+        return pc_loader(os.path.join(params.dataset_folder, data_set[k]['query']))
 
     # The reference reads and prepares every submap serially in the main process, in line with the
-    # GPU work (eval/pnv_evaluate.py:155-176).  Here the files of the NEXT batches are read and
-    # prepared by a small thread pool (numpy / torch release the GIL) while the GPU embeds the
-    # current one; results are consumed strictly in dataset order, so batch composition is unchanged.
+    # GPU work (eval/pnv_evaluate.py:155-176).  Here the files of the NEXT batches are read and prepared by a
+    # thread pool while the GPU embeds the current one, in groups of `grp` submaps per task: one vectorised
+    # prepare_batch() pass per group (bit-identical values) keeps the data cache-resident and pays the Python /
+    # dispatch cost -- which is what the pool threads queue for, holding the GIL -- once per group instead of
+    # once per submap.  Results are consumed strictly in dataset order, so batch composition is unchanged.
     workers = int(os.environ.get('HFL_LOADER_THREADS', min(16, os.cpu_count() or 1)))
+    grp = int(os.environ.get('HFL_LOADER_GROUP', 8))
+
+    def load_group(ks):
+        return prepare_batch([read(k) for k in ks], params, normalize, cyl)
+
     if workers <= 1 or not spans:
         for _, b, e in spans:
-            clouds = [load(k) for k in keys[b:e]]
+            clouds = load_group(keys[b:e])
             chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
     else:
         from concurrent.futures import ThreadPoolExecutor
-        # one intra-op thread per torch CPU op while the pool runs: the per-submap tensors are small
-        # (tens of K points) and N pool threads each fanning out to an OpenMP team oversubscribe the
-        # cores (measured on 8 cores, 8 workers: 485 -> 755 submaps/s)
+        # one intra-op thread per torch CPU op while the pool runs: the group tensors are small (a few hundred
+        # K points) and N pool threads each fanning out to an OpenMP team oversubscribe the cores
         intra = torch.get_num_threads()
         torch.set_num_threads(1)
         try:
             with ThreadPoolExecutor(max_workers=workers) as pool:
+                def batch_job(b, e):
+                    return [pool.submit(load_group, keys[i:min(i + grp, e)]) for i in range(b, e, grp)]
                 ahead = 2                                        # batches in flight on the host side
-                pending = [[pool.submit(load, k) for k in keys[b:e]] for _, b, e in spans[:ahead]]
+                pending = [batch_job(b, e) for _, b, e in spans[:ahead]]
                 for t in range(len(spans)):
-                    clouds = [f.result() for f in pending.pop(0)]
+                    clouds = [c for f in pending.pop(0) for c in f.result()]
                     if t + ahead < len(spans):
                         _, b, e = spans[t + ahead]
-                        pending.append([pool.submit(load, k) for k in keys[b:e]])
+                        pending.append(batch_job(b, e))
                     chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())
         finally:
             torch.set_num_threads(intra)

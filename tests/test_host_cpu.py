@@ -343,3 +343,38 @@ def test_get_latent_vectors_edge_cases(tmp_path, monkeypatch):
         bad = mk()
         bad.dataset_name = 'NoSuchDataset'
         E.get_latent_vectors(model, {0: {'query': 'a.bin'}}, 'cpu', bad)
+
+
+@pytest.mark.parametrize('cfg', ['wild-places', 'cs-wild-places', 'oxford'])
+def test_prepare_batch_is_bit_identical(cfg, tmp_path):
+    """The batched host prep (one vectorised pass per evaluation batch) returns exactly the arrays of the
+    per-submap prepare_cloud() -- the mirror of eval/pnv_evaluate.py:158-171 -- for clouds of very different sizes,
+    clouds that lose points to the range masks, and an empty cloud."""
+    from hotformerloc_b200.config.presets import write_configs
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    from hotformerloc_b200.misc.utils import TrainingParams
+    paths = write_configs(str(tmp_path), cfg, dataset_folder=str(tmp_path))
+    params = TrainingParams(paths['config'], paths['model_config'])
+    normalize = None
+    if params.normalize_points or params.scale_factor is not None:
+        normalize = E.Normalize(scale_factor=params.scale_factor, unit_sphere_norm=params.unit_sphere_norm)
+    cyl = E.CylindricalCoordinates(use_octree=True) \
+        if params.load_octree and params.model_params.coordinates == 'cylindrical' else None
+    rng = np.random.default_rng(3)
+    scale = 30.0 if normalize is not None else 1.0
+    raws = []
+    for n in (30000, 7, 1, 4096, 60000, 513):
+        pts = rng.uniform(-1, 1, (n, 3)) * scale * rng.uniform(0.5, 1.3)      # some clouds exceed the unit range
+        pts[:, 2] *= 0.3
+        raws.append(pts.astype(np.float64))
+    got = E.prepare_batch(raws, params, normalize, cyl)
+    assert len(got) == len(raws)
+    for g, r in zip(got, raws):
+        ref = E.prepare_cloud(r, params, normalize, cyl)
+        assert g.dtype == ref.dtype and g.shape == ref.shape
+        assert np.array_equal(g, ref)
+    # float32 inputs (the .pcd reader's xyz fast path) too
+    raws32 = [r.astype(np.float32) for r in raws[:3]]
+    for g, r in zip(E.prepare_batch(raws32, params, normalize, cyl), raws32):
+        ref = E.prepare_cloud(r, params, normalize, cyl)
+        assert g.dtype == ref.dtype and np.array_equal(g, ref)
