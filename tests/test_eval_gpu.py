@@ -105,9 +105,9 @@ def test_config4_recall_vs_oracle_golden(tmp_path):
     on-disk format (.pcd + evaluation dicts), embedded through get_latent_vectors and ranked through get_recall.
     Golden = tests/golden/config4_recall.npz: the REFERENCE'S own loaders / Normalize / CylindricalCoordinates /
     get_recall around the fp32 CPU oracle forward (oracle/make_golden_config4.py, 2048 submaps on the CPU).
-    Bars: descriptors cosine >= 0.999; recall@1, recall@1 % and MRR within 0.5 pt of the oracle's (bf16 descriptors
-    may swap a handful of near-tied candidates among 512; BASELINE.json north_star asks for 0.1 pt on REAL data,
-    where positives are not near-ties)."""
+    Bars: descriptors cosine >= 0.999; average recall@1 and recall@1 % within 0.1 pt of the oracle's (BASELINE.json
+    north_star), every recall@N and the MRR within 0.2 pt, recall@1 of each run pair within 1 pt (5 of 512 queries:
+    bf16 descriptors may swap near-tied synthetic candidates)."""
     import json
     from hotformerloc_b200.config.presets import write_configs
     from hotformerloc_b200.datasets.synthetic import make_eval_dataset
@@ -139,7 +139,11 @@ def test_config4_recall_vs_oracle_golden(tmp_path):
             assert abs(rec[0] - gold[f'recall_{m}_{n}'][0]) < 1.0, (m, n, rec[0], gold[f'recall_{m}_{n}'][0])
             recs.append(rec), oprs.append(opr), mrrs.append(mrr)
     ave = np.mean(recs, axis=0)
-    assert abs(ave[0] - gold['ave_recall'][0]) < 0.5, (ave[0], gold['ave_recall'][0])
-    assert np.abs(ave - gold['ave_recall']).max() < 0.5
-    assert abs(np.mean(oprs) - gold['ave_one_percent_recall']) < 0.5
-    assert abs(np.mean(mrrs) - gold['ave_mrr']) < 0.5
+    print('config-4 recall@1 %.4f (oracle %.4f)  recall@1%% %.4f (%.4f)  MRR %.4f (%.4f)  max |d recall@N| %.4f' % (
+        ave[0], gold['ave_recall'][0], np.mean(oprs), gold['ave_one_percent_recall'], np.mean(mrrs), gold['ave_mrr'],
+        np.abs(ave - gold['ave_recall']).max()))
+    # BASELINE.json north_star: recall@1 / recall@1 % within 0.1 pt
+    assert abs(ave[0] - gold['ave_recall'][0]) <= 0.1, (ave[0], gold['ave_recall'][0])
+    assert abs(np.mean(oprs) - gold['ave_one_percent_recall']) <= 0.1
+    assert np.abs(ave - gold['ave_recall']).max() <= 0.2
+    assert abs(np.mean(mrrs) - gold['ave_mrr']) <= 0.2
