@@ -444,23 +444,45 @@ struct PoolParams {
 };
 
 __global__ void __launch_bounds__(256) k_pool_stats(const PoolParams p) {
-  // grid: (B, ceil(kq/8)); warp = one query column, lanes stride over tokens
-  const int b = blockIdx.x, q = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (q >= p.kq) return;
+  // grid: (B, ceil(kq/32)); lane = one query column (a warp reads 32 consecutive logits of a token row: one
+  // 128-byte line), the 8 warps stride over the submap's tokens with an ONLINE (max, sum) per column -- one
+  // coalesced pass over the logits instead of two strided ones -- and are merged through shared memory
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.y * 32 + lane;
+  const bool ok = q < p.kq;
   const int64_t t0 = p.tok_off[b], t1 = p.tok_off[b + 1];
   const float sc = p.scale * 1.4426950408889634f;
-  float m = -INFINITY;
-  for (int64_t t = t0 + lane; t < t1; t += 32)
-    m = fmaxf(m, p.logits[hat_row(t, p.K) * p.ldl + q] * sc);
+  const uint32_t K = (uint32_t)p.K;
+  float m = -INFINITY, s = 0.f;
+  // four tokens in flight per warp
+  for (int64_t t = t0 + warp * 4; t < t1; t += 32) {
+    float v[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float s = 0.f;
-  for (int64_t t = t0 + lane; t < t1; t += 32)
-    s += exp2f(p.logits[hat_row(t, p.K) * p.ldl + q] * sc - m);
-  s = warp_sum(s);
-  if (lane == 0) {
-    p.stat[((size_t)b * p.kq + q) * 2] = m;
-    p.stat[((size_t)b * p.kq + q) * 2 + 1] = s > 0.f ? 1.0f / s : 0.f;
+    for (int u = 0; u < 4; ++u) {
+      const int64_t tt = t + u;
+      const bool in = ok && tt < t1;
+      const int64_t row = in ? (K ? tt + (int64_t)((uint32_t)tt / K) + 1 : tt) : 0;
+      v[u] = in ? __ldg(p.logits + row * p.ldl + q) * sc : -INFINITY;
+    }
+    const float mn = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), m);
+    if (mn > -INFINITY) {
+      s = s * exp2f(m - mn) + exp2f(v[0] - mn) + exp2f(v[1] - mn) + exp2f(v[2] - mn) + exp2f(v[3] - mn);
+      m = mn;
+    }
+  }
+  __shared__ float sm[8][32], ss[8][32];
+  sm[warp][lane] = m;
+  ss[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && ok) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, sm[w][lane]);
+    float S = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) S += sm[w][lane] > -INFINITY ? ss[w][lane] * exp2f(sm[w][lane] - M) : 0.f;
+    p.stat[((size_t)b * p.kq + q) * 2] = M;
+    p.stat[((size_t)b * p.kq + q) * 2 + 1] = S > 0.f ? 1.0f / S : 0.f;
   }
 }
 
@@ -748,7 +770,7 @@ int hfl_attn_pool(const float* logits, const float* x, const void* xb, const int
   HFL_CHECK_ARG(logits && xb && tok_off && stat && out, "null argument");
   HFL_CHECK_ARG(C == 256, "C must be 256");
   PoolParams p{logits, x, (const __nv_bfloat16*)xb, tok_off, stat, out, B, kq, ldl, K, C, ktot, q_off, scale};
-  HFL_LAUNCH((k_pool_stats<<<dim3(B, (kq + 7) / 8), 256, 0, st>>>(p)));
+  HFL_LAUNCH((k_pool_stats<<<dim3(B, (kq + 31) / 32), 256, 0, st>>>(p)));
   HFL_ENSURE_SMEM(PM_SMEM, k_pool_mma);
   HFL_LAUNCH((k_pool_mma<<<dim3(B, (kq + PM_Q - 1) / PM_Q), 256, PM_SMEM, st>>>(p)));
   return HFL_OK;
