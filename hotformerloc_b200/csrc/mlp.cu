@@ -181,6 +181,53 @@ __device__ __forceinline__ void ml_epi2_slice(const MlpParams& p, int tile, int 
   __syncwarp();                                              // the stage is free again
 }
 
+// Same for the store warps of the block kernel, in 32-column units: the 2 KB stage takes 16 rows x 128 B at a time
+// (16-byte chunk c of row r at c ^ (r & 7)); after the transposition 8 lanes hold one row's 128 contiguous bytes,
+// so every fp32 store instruction writes FOUR FULL LINES (the 16-column form writes eight half lines: twice the
+// wavefronts on the SM's store path, which is what bounds this epilogue) and every bf16 store four 64-byte pieces.
+template <int C>
+__device__ __forceinline__ void ml_epi2_slice32(const MlpParams& p, int tile, int quad, int lane, uint32_t lane_base,
+                                                uint32_t stage, int col0, uint32_t arrive_bar) {
+  const int ch = lane & 7;
+  uint32_t raw[32];
+  ptx::tmem_ld32(lane_base + 256 + col0, raw);
+  ptx::tmem_ld_wait();
+  if (arrive_bar) {                                          // acc2 fully read by this warp
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(arrive_bar);
+  }
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {                     // rows 0-15, then 16-31 of the quadrant
+    __syncwarp();                                            // the previous pass's transposed loads have completed
+    if ((lane >> 4) == hrow) {
+      const int lr = lane & 15;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        ml_sts128(stage + (uint32_t)lr * 128u + (uint32_t)((c ^ (lr & 7)) << 4), raw[4 * c], raw[4 * c + 1],
+                  raw[4 * c + 2], raw[4 * c + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 3) + 4 * i;                    // row of this pass, 8 lanes per row
+      const uint4 a = ml_lds128(stage + (uint32_t)rr * 128u + (uint32_t)((ch ^ (rr & 7)) << 4));
+      const int orr = tile * ML_BM + quad * 32 + hrow * 16 + rr;
+      if (orr < p.M) {
+        const size_t col = (size_t)(col0 + ch * 4);
+        if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(p.out_f32 + (size_t)orr * C + col) = a;
+        if (p.out_bf16 && !(p.dbg & 2)) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(a.x), __uint_as_float(a.y));
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(a.z), __uint_as_float(a.w));
+          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)orr * C + col) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int C, bool PJ = false>
 struct MlpSmem {
   static constexpr int KB1 = C / 64;                 // K blocks of GEMM 1
@@ -352,7 +399,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
         ptx::tc_fence_after();
 #pragma unroll 1
         for (int sl = 0; sl < C / 32; ++sl)
-          ml_epi2_slice<C>(p, blockIdx.x + it * gridDim.x, q2, lane, lb2, st2, sl * 32, sl + 1 == C / 32 ? c2_empty : 0u);
+          ml_epi2_slice32<C>(p, blockIdx.x + it * gridDim.x, q2, lane, lb2, st2, sl * 32, sl + 1 == C / 32 ? c2_empty : 0u);
       }
     }
     const int pt = (warp - 9) * 32 + lane;
