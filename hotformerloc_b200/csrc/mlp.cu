@@ -186,17 +186,9 @@ __device__ __forceinline__ void ml_epi2_slice(const MlpParams& p, int tile, int 
 // so every fp32 store instruction writes FOUR FULL LINES (the 16-column form writes eight half lines: twice the
 // wavefronts on the SM's store path, which is what bounds this epilogue) and every bf16 store four 64-byte pieces.
 template <int C>
-__device__ __forceinline__ void ml_epi2_slice32(const MlpParams& p, int tile, int quad, int lane, uint32_t lane_base,
-                                                uint32_t stage, int col0, uint32_t arrive_bar) {
+__device__ __forceinline__ void ml_epi2_slice32(const MlpParams& p, int tile, int quad, int lane, uint32_t stage,
+                                                int col0, const uint32_t (&raw)[32]) {
   const int ch = lane & 7;
-  uint32_t raw[32];
-  ptx::tmem_ld32(lane_base + 256 + col0, raw);
-  ptx::tmem_ld_wait();
-  if (arrive_bar) {                                          // acc2 fully read by this warp
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(arrive_bar);
-  }
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {                     // rows 0-15, then 16-31 of the quadrant
     __syncwarp();                                            // the previous pass's transposed loads have completed
@@ -397,9 +389,20 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       for (int it = 0; it < n_my; ++it) {
         ptx::mbar_wait_sleep(c2_full, it & 1, 64);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int sl = 0; sl < C / 32; ++sl)
-          ml_epi2_slice32<C>(p, blockIdx.x + it * gridDim.x, q2, lane, lb2, st2, sl * 32, sl + 1 == C / 32 ? c2_empty : 0u);
+        // the next 32-column slice is in flight from tensor memory while the current one is transposed and stored
+        uint32_t raw[2][32];
+        ptx::tmem_ld32(lb2 + 256, raw[0]);
+#pragma unroll
+        for (int sl = 0; sl < C / 32; ++sl) {
+          ptx::tmem_ld_wait();
+          if (sl + 1 < C / 32) ptx::tmem_ld32(lb2 + 256 + (sl + 1) * 32, raw[(sl + 1) & 1]);
+          else {                                             // acc2 fully read by this warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(c2_empty);
+          }
+          ml_epi2_slice32<C>(p, blockIdx.x + it * gridDim.x, q2, lane, st2, sl * 32, raw[sl & 1]);
+        }
       }
     }
     const int pt = (warp - 9) * 32 + lane;
