@@ -144,6 +144,36 @@ def prepare_batch(raws: List[np.ndarray], params: TrainingParams, normalize=None
     return out
 
 
+def device_prep_supported(normalize, cyl) -> bool:
+    """The opt-in device-side prep (HFL_DEVICE_PREP=1, hfl_prepare_clouds) covers the bounding-box / fixed-scale
+    Normalize and CylindricalCoordinates(use_octree=True) on fp32 clouds."""
+    return normalize is None or not normalize.unit_sphere_norm
+
+
+def prepare_batch_device(raws: List[np.ndarray], params: TrainingParams, normalize, cyl, device):
+    """prepare_batch() on the device: raw fp32 clouds -> one pinned H2D copy -> Normalize / masks / cylindrical /
+    compaction kernels.  Returns (points, offsets, n_ticket): device tensors for build_batch_device and a pinned
+    count + event the caller waits for right before the build (the point count after the masks is the one
+    host-side number the octree build needs).  Values are bit-identical to prepare_cloud() except where the CPU's
+    sqrt / atan2 kernels and CUDA's differ in the last bit (see csrc/prep.cu); hence opt-in."""
+    from .. import ops
+    lens = np.array([len(r) for r in raws], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    host = torch.empty((int(off[-1]), 3), dtype=torch.float32).pin_memory()
+    np.concatenate(raws, axis=0, out=host.numpy())
+    pts = host.to(device, non_blocking=True)
+    offd = torch.from_numpy(off).to(device, non_blocking=True)
+    out, off_out, total = ops.prepare_clouds(
+        pts, offd, norm=normalize is not None, zero_mean=normalize.zero_mean if normalize is not None else True,
+        scale_factor=normalize.scale_factor if normalize is not None else None,
+        norm_range=normalize.norm_range if normalize is not None else 1.0, cyl=cyl is not None)
+    n_pin = torch.empty(1, dtype=torch.int32).pin_memory()
+    n_pin.copy_(total, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return out, off_out, (n_pin, ev, host)
+
+
 def collate_batch(data: List[np.ndarray], device, params: TrainingParams):
     """One merged, neighbour-complete, device-resident octree for a list of prepared clouds."""
     return {'octree': build_batch(data, params.octree_depth, 2, device)}
@@ -229,11 +259,37 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
     # once per submap.  Results are consumed strictly in dataset order, so batch composition is unchanged.
     workers = int(os.environ.get('HFL_LOADER_THREADS', min(16, os.cpu_count() or 1)))
     grp = int(os.environ.get('HFL_LOADER_GROUP', 8))
+    if os.environ.get('HFL_DEVICE_PREP', '0') == '1' and device_prep_supported(normalize, cyl):
+        # opt-in: the pool threads only read files; Normalize / masks / cylindrical run on the GPU for the whole
+        # batch (hfl_prepare_clouds), the prepared points never visit the host
+        from concurrent.futures import ThreadPoolExecutor
+        from ..octree import build_batch_device
+        with ThreadPoolExecutor(max_workers=max(workers, 1)) as pool:
+            def read_job(b, e):
+                return [pool.submit(read, k) for k in keys[b:e]]
+            ahead = 2
+            pending = [read_job(b, e) for _, b, e in spans[:ahead]]
+            staged = []
+            for t in range(len(spans)):
+                raws = [np.ascontiguousarray(f.result(), dtype=np.float32) for f in pending.pop(0)]
+                if t + ahead < len(spans):
+                    _, b, e = spans[t + ahead]
+                    pending.append(read_job(b, e))
+                staged.append(prepare_batch_device(raws, params, normalize, cyl, device))
+                if len(staged) > 1 or t == len(spans) - 1:     # embed batch t - 1 while batch t's prep is in flight
+                    while staged and (len(staged) > 1 or t == len(spans) - 1):
+                        pts, off, (n_pin, ev, _host) = staged.pop(0)
+                        ev.synchronize()
+                        o = build_batch_device(pts[:int(n_pin[0])], off, params.octree_depth, 2)
+                        chunks.append(compute_embedding(model, {'octree': o}).float())
+        workers = -1                                             # done
 
     def load_group(ks):
         return prepare_batch([read(k) for k in ks], params, normalize, cyl)
 
-    if workers <= 1 or not spans:
+    if workers == -1:
+        pass
+    elif workers <= 1 or not spans:
         for _, b, e in spans:
             clouds = load_group(keys[b:e])
             chunks.append(compute_embedding(model, collate_batch(clouds, device, params)).float())

@@ -116,6 +116,7 @@ SIGNATURES = {
     'hfl_gem_pool': (C.c_int, [_p, _p, _i32, _i32, _i32, _f32, _f32, _p, _i32, _i32, _p]),
     'hfl_gem_head': (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _f32, _i32, _i32, _p, _p]),
     'hfl_knn_topk': (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    'hfl_prepare_clouds': (C.c_int, [_p, _p, _i32, _i64, _i32, _i32, _f32, _f32, _i32, _p, _p, _p, _p, _p, _p]),
     'hfl_knn_workspace_bytes': (C.c_int64, [_i32, _i32, _i32]),
     'hfl_knn_topk_ws': (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i64, _p]),
     'hfl_topk_merge': (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),

@@ -132,6 +132,26 @@ def gem_head(pooled, w, bn_g, bn_b, bn_mean, bn_var, bn_eps, normalize, out):
                                  _p(bn_var), float(bn_eps), w.shape[0], int(normalize), _p(out), _s()))
 
 
+def prepare_clouds(pts: torch.Tensor, off: torch.Tensor, *, norm: bool, zero_mean: bool = True,
+                   scale_factor=None, norm_range: float = 1.0, cyl: bool = False):
+    """Device-side Normalize / range masks / CylindricalCoordinates + compaction of a batch of raw fp32 clouds
+    (hfl_prepare_clouds).  Returns (points [n_in, 3] fp32 of which the first off_out[-1] rows are valid,
+    off_out [B + 1] int32, total [1] int32 device tensor)."""
+    assert pts.dtype == torch.float32 and off.dtype == torch.int32
+    n_in, B = pts.shape[0], off.numel() - 1
+    dev = pts.device
+    tmp = torch.empty_like(pts)
+    out = torch.empty_like(pts)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    off_out = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    N.check(N.lib().hfl_prepare_clouds(_p(pts), _p(off), B, n_in, int(norm), int(zero_mean),
+                                       float(scale_factor) if scale_factor is not None else 0.0,
+                                       float(norm_range if norm_range is not None else 1.0), int(cyl), _p(tmp),
+                                       _p(cnt), _p(out), _p(off_out), _p(total), _s()))
+    return out, off_out, total
+
+
 def knn_topk(q: torch.Tensor, db: torch.Tensor, k: int = 25, idx_offset: int = 0):
     """Exact L2 top-k of every query row against a database shard; returns
     (squared distances [nq,k] fp32, indices [nq,k] int32) sorted by (dist, idx)."""

@@ -209,6 +209,19 @@ int hfl_gem_head(const float* pooled, int32_t B, int32_t in_dim, const float* w,
                  const float* bn_b, const float* bn_mean, const float* bn_var, float bn_eps,
                  int32_t out_dim, int32_t normalize, float* out, void* stream);
 
+/* OPT-IN device-side form of the pre-octree transforms of the evaluation loop (eval/pnv_evaluate.py:158-171):
+ * Normalize, bounding-box form (datasets/augmentation.py:212-235) -> |coord| <= 1 mask -> [radial mask ->
+ * CylindricalCoordinates(use_octree=True), datasets/coordinate_utils.py:68-116] -> stable per-cloud compaction.
+ * in: [n_in*3] raw fp32 points of B clouds back to back, off_in [B+1].  tmp: [n_in*3], cnt: [B] scratch.
+ * out: [<= n_in*3] prepared points, off_out: [B+1] their offsets = the inputs of hfl_octree_build;
+ * total_out (optional, e.g. mapped / pinned host memory): number of prepared points.
+ * scale_factor > 0: coords / scale_factor, else coords * (2 norm_range / (max extent + 1e-6)).
+ * Bit-identical to the host path except for sqrt / atan2, where torch's CPU kernels are not correctly rounded
+ * (last-bit differences, see csrc/prep.cu and DESIGN.md section 6). */
+int hfl_prepare_clouds(const float* in, const int32_t* off_in, int32_t B, int64_t n_in, int32_t norm,
+                       int32_t zero_mean, float scale_factor, float norm_range, int32_t cyl, float* tmp,
+                       int32_t* cnt, float* out, int32_t* off_out, int32_t* total_out, void* stream);
+
 /* Exact L2 top-k (eval/pnv_evaluate.py:200-225, 245) on one database shard, and the
  * merge of all-gathered partial lists. */
 int hfl_knn_topk(const float* q, int32_t nq, const float* db, int32_t ndb, int32_t dim, int32_t k,

@@ -147,3 +147,67 @@ def test_config4_recall_vs_oracle_golden(tmp_path):
     assert abs(np.mean(oprs) - gold['ave_one_percent_recall']) <= 0.1
     assert np.abs(ave - gold['ave_recall']).max() <= 0.2
     assert abs(np.mean(mrrs) - gold['ave_mrr']) <= 0.2
+
+
+@pytest.mark.parametrize('cfg', ['wild-places', 'cs-wild-places'])
+def test_device_prep_matches_host_prep(cfg, tmp_path):
+    """hfl_prepare_clouds (opt-in device-side Normalize / masks / CylindricalCoordinates / compaction) against the host
+    mirror of eval/pnv_evaluate.py:158-171 on clouds of very different sizes, some losing points to the masks: same
+    survivors in the same order; the normalised and height coordinates bit-identical; the radial coordinate (sqrt: torch's
+    CPU kernel is not correctly rounded) within an ulp or two of rho (5e-7 after the rescale) and identical for most
+    points (98-99 % on the AVX-512 hosts measured); the heading coordinate (atan2: CUDA libm vs the CPU's vectorised
+    routine) within 4 ulp and identical for a large part of the points (73 % measured); octree keys of the two inputs identical on all but a vanishing fraction of nodes."""
+    from hotformerloc_b200 import ops
+    from hotformerloc_b200.config.presets import write_configs
+    from hotformerloc_b200.eval import pnv_evaluate as E
+    from hotformerloc_b200.misc.utils import TrainingParams
+    from hotformerloc_b200.octree import build_batch, build_batch_device
+    paths = write_configs(str(tmp_path), cfg, dataset_folder=str(tmp_path))
+    params = TrainingParams(paths['config'], paths['model_config'])
+    normalize = E.Normalize(scale_factor=params.scale_factor, unit_sphere_norm=params.unit_sphere_norm) \
+        if (params.normalize_points or params.scale_factor is not None) else None
+    cyl = E.CylindricalCoordinates(use_octree=True) \
+        if params.load_octree and params.model_params.coordinates == 'cylindrical' else None
+    assert E.device_prep_supported(normalize, cyl)
+    rng = np.random.default_rng(5)
+    scale = 30.0 if normalize is not None else 1.0
+    raws = []
+    for n in (30000, 7, 1, 4096, 60000, 513):
+        pts = rng.uniform(-1, 1, (n, 3)) * scale * rng.uniform(0.5, 1.3)
+        pts[:, 2] *= 0.3
+        raws.append(pts.astype(np.float32))
+    host = [E.prepare_cloud(r, params, normalize, cyl) for r in raws]
+    out, off, (n_pin, ev, _) = E.prepare_batch_device(raws, params, normalize, cyl, 'cuda')
+    ev.synchronize()
+    off = off.cpu().numpy()
+    assert int(n_pin[0]) == off[-1] == sum(len(h) for h in host)
+    dev = out[:off[-1]].cpu().numpy()
+    exact = total = 0
+    for b, h in enumerate(host):
+        d = dev[off[b]:off[b + 1]]
+        assert d.shape == h.shape, (b, d.shape, h.shape)
+        if len(h) == 0:
+            continue
+        cols = (2,) if cyl is not None else (0, 1, 2)
+        for c in cols:
+            assert np.array_equal(d[:, c], h[:, c]), (b, c)
+        if cyl is not None:
+            assert np.abs(d[:, 0].astype(np.float64) - h[:, 0]).max() <= 5e-7
+            assert (d[:, 0] == h[:, 0]).mean() >= 0.9 or len(h) < 100
+            ulp = np.abs(d[:, 1].view(np.int32).astype(np.int64) - h[:, 1].view(np.int32).astype(np.int64))
+            assert ulp.max() <= 4, ulp.max()               # 1 ulp (CPU routine) + 2 ulp (CUDA libm) + rescale rounding
+            exact += int((ulp == 0).sum())
+            total += len(ulp)
+    if cyl is not None:
+        print(f'heading coordinate bit-identical for {exact}/{total} points')
+        assert exact >= 0.3 * total
+    big = [h for h in host if len(h) > 0]
+    o_host = build_batch(big, params.octree_depth, 2, 'cuda').finalize()
+    keep = [b for b, h in enumerate(host) if len(h) > 0]
+    sel = torch.cat([out[off[b]:off[b + 1]] for b in keep])
+    o2 = torch.tensor(np.concatenate([[0], np.cumsum([off[b + 1] - off[b] for b in keep])]), dtype=torch.int32, device='cuda')
+    o_dev = build_batch_device(sel, o2, params.octree_depth, 2).finalize()
+    D = params.octree_depth
+    kh, kd = o_host.keys[D].cpu().numpy(), o_dev.keys[D].cpu().numpy()
+    common = np.intersect1d(kh, kd).size
+    assert common >= 0.999 * max(kh.size, kd.size), (common, kh.size, kd.size)
