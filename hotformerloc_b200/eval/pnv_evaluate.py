@@ -150,18 +150,48 @@ def device_prep_supported(normalize, cyl) -> bool:
     return normalize is None or not normalize.unit_sphere_norm
 
 
-def prepare_batch_device(raws: List[np.ndarray], params: TrainingParams, normalize, cyl, device):
+class _PinnedStage:
+    """Reusable pinned staging buffers for the raw points of a batch (allocating + pinning tens of MB per batch costs
+    more host time than the copy itself)."""
+
+    def __init__(self):
+        self.free = []
+
+    def take(self, n_points: int) -> torch.Tensor:
+        for i, t in enumerate(self.free):
+            if t.shape[0] >= n_points:
+                return self.free.pop(i)
+        return torch.empty((max(n_points, 1) * 5 // 4, 3), dtype=torch.float32).pin_memory()
+
+    def give(self, t: torch.Tensor) -> None:
+        if len(self.free) < 4:
+            self.free.append(t)
+
+
+_PINNED = _PinnedStage()
+
+
+def stage_raw_batch(raws: List[np.ndarray]):
+    """Host half of the device-side prep (runs on a worker thread): the raw fp32 clouds of a batch packed back to
+    back into a pinned staging buffer + their offsets."""
+    lens = np.array([len(r) for r in raws], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n = int(off[-1])
+    host = _PINNED.take(n)
+    if n:
+        np.concatenate([np.asarray(r, dtype=np.float32) for r in raws], axis=0, out=host[:n].numpy())
+    return host, n, off
+
+
+def prepare_batch_device(raws, params: TrainingParams, normalize, cyl, device, staged=None):
     """prepare_batch() on the device: raw fp32 clouds -> one pinned H2D copy -> Normalize / masks / cylindrical /
     compaction kernels.  Returns (points, offsets, n_ticket): device tensors for build_batch_device and a pinned
     count + event the caller waits for right before the build (the point count after the masks is the one
     host-side number the octree build needs).  Values are bit-identical to prepare_cloud() except where the CPU's
     sqrt / atan2 kernels and CUDA's differ in the last bit (see csrc/prep.cu); hence opt-in."""
     from .. import ops
-    lens = np.array([len(r) for r in raws], dtype=np.int64)
-    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
-    host = torch.empty((int(off[-1]), 3), dtype=torch.float32).pin_memory()
-    np.concatenate(raws, axis=0, out=host.numpy())
-    pts = host.to(device, non_blocking=True)
+    host, n, off = staged if staged is not None else stage_raw_batch(raws)
+    pts = host[:n].to(device, non_blocking=True)
     offd = torch.from_numpy(off).to(device, non_blocking=True)
     out, off_out, total = ops.prepare_clouds(
         pts, offd, norm=normalize is not None, zero_mean=normalize.zero_mean if normalize is not None else True,
@@ -264,24 +294,30 @@ def get_latent_vectors(model, data_set, device, params: TrainingParams):
         # batch (hfl_prepare_clouds), the prepared points never visit the host
         from concurrent.futures import ThreadPoolExecutor
         from ..octree import build_batch_device
-        with ThreadPoolExecutor(max_workers=max(workers, 1)) as pool:
-            def read_job(b, e):
-                return [pool.submit(read, k) for k in keys[b:e]]
-            ahead = 2
-            pending = [read_job(b, e) for _, b, e in spans[:ahead]]
+        with ThreadPoolExecutor(max_workers=max(workers, 1)) as pool, ThreadPoolExecutor(max_workers=2) as stager:
+            def stage_job(b, e):
+                files = [pool.submit(read, k) for k in keys[b:e]]
+                return stager.submit(lambda: stage_raw_batch([f.result() for f in files]))
+            ahead = 3                                            # batches in flight on the host side
+            pending = [stage_job(b, e) for _, b, e in spans[:ahead]]
             staged = []
+
+            def embed_oldest():
+                pts, off, (n_pin, ev, host) = staged.pop(0)
+                ev.synchronize()                                 # H2D + prep kernels of that batch are done
+                _PINNED.give(host)
+                o = build_batch_device(pts[:int(n_pin[0])], off, params.octree_depth, 2)
+                chunks.append(compute_embedding(model, {'octree': o}).float())
             for t in range(len(spans)):
-                raws = [np.ascontiguousarray(f.result(), dtype=np.float32) for f in pending.pop(0)]
+                st = pending.pop(0).result()
                 if t + ahead < len(spans):
                     _, b, e = spans[t + ahead]
-                    pending.append(read_job(b, e))
-                staged.append(prepare_batch_device(raws, params, normalize, cyl, device))
-                if len(staged) > 1 or t == len(spans) - 1:     # embed batch t - 1 while batch t's prep is in flight
-                    while staged and (len(staged) > 1 or t == len(spans) - 1):
-                        pts, off, (n_pin, ev, _host) = staged.pop(0)
-                        ev.synchronize()
-                        o = build_batch_device(pts[:int(n_pin[0])], off, params.octree_depth, 2)
-                        chunks.append(compute_embedding(model, {'octree': o}).float())
+                    pending.append(stage_job(b, e))
+                staged.append(prepare_batch_device(None, params, normalize, cyl, device, staged=st))
+                if len(staged) > 1:                              # embed batch t - 1 while batch t's prep is in flight
+                    embed_oldest()
+            while staged:
+                embed_oldest()
         workers = -1                                             # done
 
     def load_group(ks):
