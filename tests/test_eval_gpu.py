@@ -99,7 +99,8 @@ def test_evaluate_end_to_end_vs_oracle(tmp_path):
     assert 'Split: [' in open(os.path.join(root, 'res_splits.txt')).read()
 
 
-def test_config4_recall_vs_oracle_golden(tmp_path):
+@pytest.mark.parametrize('device_prep', [False, True])
+def test_config4_recall_vs_oracle_golden(tmp_path, monkeypatch, device_prep):
     """BASELINE.json configs[3] on the 4 x 512 subset SURVEY.md section 8d names: Wild-Places cfg (cylindrical
     coordinates, K = 48, val_batch_size 128), 4 traversals x 512 places x 30 k points written in the reference's
     on-disk format (.pcd + evaluation dicts), embedded through get_latent_vectors and ranked through get_recall.
@@ -107,8 +108,11 @@ def test_config4_recall_vs_oracle_golden(tmp_path):
     get_recall around the fp32 CPU oracle forward (oracle/make_golden_config4.py, 2048 submaps on the CPU).
     Bars: descriptors cosine >= 0.999; average recall@1 and recall@1 % within 0.1 pt of the oracle's (BASELINE.json
     north_star), every recall@N and the MRR within 0.2 pt, recall@1 of each run pair within 1 pt (5 of 512 queries:
-    bf16 descriptors may swap near-tied synthetic candidates)."""
+    bf16 descriptors may swap near-tied synthetic candidates).  device_prep: the same with the opt-in device-side
+    Normalize / cylindrical transform (HFL_DEVICE_PREP=1) -- the last-bit sqrt / atan2 differences must not move
+    the recall out of the same tolerance."""
     import json
+    monkeypatch.setenv('HFL_DEVICE_PREP', '1' if device_prep else '0')
     from hotformerloc_b200.config.presets import write_configs
     from hotformerloc_b200.datasets.synthetic import make_eval_dataset
     from hotformerloc_b200.eval import pnv_evaluate as E
