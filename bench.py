@@ -149,7 +149,7 @@ def kernel_profile(model, octree_fn):
         return {'flop': 2.0 * M * C * C + 4.0 * M * W1.shape[0] * W1.shape[1],
                 'byte': float(M * C * (2 + 4 + 4 + (2 if k.get('out_bf16') is not None else 0)))}
 
-    def qkv_attn_work(y, Wg, bg, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
+    def qkv_attn_work(y, Wg, bg, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale, codes=None):
         L = K + (1 if hat else 0)
         rows = n_win * L
         return {'flop': 2.0 * rows * C * 3 * C + 4.0 * n_win * L * L * C,
@@ -160,7 +160,7 @@ def kernel_profile(model, octree_fn):
     for name, work in patches.items():
         saved[name] = getattr(ops, name)
         setattr(ops, name, wrap(name, saved[name], work))
-    others = ['varlen_attn', 'stem_conv', 'ln_rows', 'rt_init', 'attn_pool', 'mixer_tail',
+    others = ['varlen_attn', 'stem_conv', 'ln_rows', 'rt_init', 'attn_pool', 'mixer_tail', 'qkv_attn_codes',
               'hat_rows', 'remap_hat']
     for name in others:
         saved[name] = getattr(ops, name)

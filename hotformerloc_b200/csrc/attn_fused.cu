@@ -73,6 +73,8 @@ struct QaParams {
   int n_win, H, K, dil, hat, bnd, subp;
   float scale;
   long long* prof;             // diagnostics only (HFL_QA_PROF): per-role wait / work cycles of CTA 0
+  const uint32_t* codes;       // optional [n_win, L, LP] pair codes (hfl_qkv_attn_codes): block-invariant, made once per level
+  int lp;                      // padded row length of `codes` (multiple of 4)
 };
 
 __device__ __forceinline__ void qa_sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -452,7 +454,27 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
     for (int gi = 0; gi < total; ++gi) {
       const int it = gi / G, grp = gi - it * G;
       const uint32_t gcount = (uint32_t)gi;
-      if (grp == 0) {
+      if (grp == 0 && p.codes != nullptr) {
+        // pair codes made once per level by k_pair_codes (they do not depend on the block): 16-byte loads of this
+        // row's codes; both head parities of a query read the same line
+        const int tile = blockIdx.x + it * gridDim.x;
+        const long long t_codes = PROF ? clock64() : 0;
+        const int w = tile * 2 + ws;
+        valid = w < p.n_win && sl < L;
+        if (hat) row = (int64_t)w * L + sl;
+        else if (dil > 1) row = (int64_t)(w / dil) * K * dil + (int64_t)sl * dil + (w % dil);
+        else row = (int64_t)w * K + sl;
+        const uint4* cp = reinterpret_cast<const uint4*>(p.codes + ((size_t)(valid ? w : 0) * L + (valid ? sl : 0)) * p.lp);
+#pragma unroll
+        for (int j4 = 0; j4 < (NKEY + 3) / 4; ++j4) {
+          const uint4 c = __ldg(cp + j4);
+          if (4 * j4 < NKEY) code[4 * j4] = c.x;
+          if (4 * j4 + 1 < NKEY) code[4 * j4 + 1] = c.y;
+          if (4 * j4 + 2 < NKEY) code[4 * j4 + 2] = c.z;
+          if (4 * j4 + 3 < NKEY) code[4 * j4 + 3] = c.w;
+        }
+        if (PROF) lacc[7] += clock64() - t_codes;
+      } else if (grp == 0) {
         const int tile = blockIdx.x + it * gridDim.x;
         // token table of the tile: thread r of team 0 loads the token of y-tile row r (window r / 64, slot r % 64)
         if (team == 0) {
@@ -638,6 +660,40 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
   }
 }
 
+// Pair codes of a level, once for all its blocks: codes[w][s][j] = x | y << 10 | z << 20 byte offsets of the
+// (query s, key j) pair of window w into the RPE tables of k_qkv_attn (slot num = zero bias: no RPE for the relay
+// token; slot num + 1 of the x axis = -inf: different submaps).  Rows are padded to lp = 4 ceil(L / 4) entries.
+__global__ void __launch_bounds__(256) k_pair_codes(const short4* __restrict__ xyzb, uint32_t* __restrict__ codes,
+                                                    int n_win, int K, int hat, int dil, int bnd, int use_rpe, int lp) {
+  __shared__ int4 tk[64];
+  const int w = blockIdx.x, L = K + hat;
+  const int num = 2 * bnd + 1, o_zero = num * 4, o_inf = (num + 1) * 4, bnd4 = bnd * 4;
+  for (int s = threadIdx.x; s < L; s += blockDim.x) {
+    int64_t t;
+    if (hat) t = (int64_t)w * K + (s == 0 ? 0 : s - 1);
+    else if (dil > 1) t = (int64_t)(w / dil) * K * dil + (int64_t)s * dil + (w % dil);
+    else t = (int64_t)w * K + s;
+    const short4 v = __ldg(xyzb + t);
+    tk[s] = make_int4(4 * (int)v.x, 4 * (int)v.y, 4 * (int)v.z, (int)v.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * lp; i += blockDim.x) {
+    const int s = i / lp, j = i - s * lp;
+    uint32_t a = 0;
+    if (j < L) {
+      const int4 me = tk[s], kj = tk[j];
+      const int ox = min(max(me.x - kj.x, -bnd4), bnd4) + bnd4;
+      const int oy = min(max(me.y - kj.y, -bnd4), bnd4) + bnd4;
+      const int oz = min(max(me.z - kj.z, -bnd4), bnd4) + bnd4;
+      const bool norel = !use_rpe || (hat && (s == 0 || j == 0));
+      a = (uint32_t)ox | ((uint32_t)oy << 10) | ((uint32_t)oz << 20);
+      if (norel) a = (uint32_t)o_zero | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
+      if (me.w != kj.w) a = (uint32_t)o_inf | ((uint32_t)o_zero << 10) | ((uint32_t)o_zero << 20);
+    }
+    codes[((size_t)w * L + s) * lp + j] = a;
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -705,9 +761,25 @@ int hfl_qkv_attn_supported(int32_t H, int32_t C, int32_t K, int32_t dil, int32_t
   return smem <= 227 * 1024;
 }
 
+int64_t hfl_qkv_attn_codes_bytes(int64_t n_win, int32_t K, int32_t hat) {
+  const int L = K + (hat ? 1 : 0);
+  return n_win * L * (int64_t)((L + 3) & ~3) * 4;
+}
+
+int hfl_qkv_attn_codes(const int16_t* xyzb, int64_t n_win, int32_t K, int32_t dil, int32_t hat, int32_t bnd,
+                       int32_t use_rpe, uint32_t* codes, void* stream_) {
+  if (n_win == 0) return HFL_OK;
+  const int L = K + (hat ? 1 : 0);
+  HFL_CHECK_ARG(xyzb && codes, "null argument");
+  HFL_CHECK_ARG(L <= 64 && dil >= 1 && (!hat || dil == 1) && n_win % dil == 0 && (2 * bnd + 3) <= 256, "bad window shape");
+  HFL_LAUNCH((k_pair_codes<<<(unsigned)n_win, 256, 0, (cudaStream_t)stream_>>>((const short4*)xyzb, codes, (int)n_win, K,
+                                                                            hat ? 1 : 0, dil, bnd, use_rpe, (L + 3) & ~3)));
+  return HFL_OK;
+}
+
 int hfl_qkv_attn(const void* y, const void* Wg, const float* bias_g, void* out, const int16_t* xyzb,
                  const float* rpe, int64_t n_win, int64_t rows, int32_t H, int32_t C, int32_t K, int32_t dil,
-                 int32_t hat, int32_t bnd, float scale, void* stream_) {
+                 int32_t hat, int32_t bnd, float scale, const uint32_t* codes, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (n_win == 0) return HFL_OK;
   HFL_CHECK_ARG(y && Wg && bias_g && out && xyzb, "null argument");
@@ -742,6 +814,8 @@ int hfl_qkv_attn(const void* y, const void* Wg, const float* bias_g, void* out, 
   p.subp = (2 * bnd + 3 + 3) & ~3;
   p.scale = scale;
   p.prof = nullptr;
+  p.codes = codes;
+  p.lp = (K + (hat ? 1 : 0) + 3) & ~3;
   const int nkey = K + p.hat;
   const int smem = (C == 128 ? QaSmem<128>::OFF_TAB : QaSmem<256>::OFF_TAB) + 3 * (H / 2) * p.subp * 4;
 #define HFL_QA_CASE(C_, NK_) \

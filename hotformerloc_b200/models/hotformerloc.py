@@ -450,8 +450,13 @@ class _Engine:
         ops.cpe_ln(x, xb, ne, cw, cg, cb, bw['n1'][0], bw['n1'][1], y, None, n, rows, C,
                    K if hat else 0)
         if _fused_attn() and 'qkv_g' in bw and ops.qkv_attn_supported(H, C, K, bw['dil'], hat, bw['bnd']):
+            # the (query, key) pair codes depend on the token positions only: one array per level and window shape,
+            # shared by all its blocks in this forward
+            ck = ('codes', tok.data_ptr(), K, bw['dil'], hat, bw['bnd'], bw['rpe'] is None)
+            if ck not in bufs:
+                bufs[ck] = ops.qkv_attn_codes(tok, n_win, K, bw['dil'], hat, bw['bnd'], bw['rpe'] is not None)
             ops.qkv_attn(y, bw['qkv_g'][0], bw['qkv_g'][1], o, tok, bw['rpe'], n_win, H, C, K, bw['dil'],
-                         hat, bw['bnd'], 0.25)
+                         hat, bw['bnd'], 0.25, codes=bufs[ck])
         else:
             ops.gather_gemm(y, bw['qkv'][0], bias=bw['qkv'][1], out_v_bf16=qkv)
             ops.window_attn(qkv, o, tok, bw['rpe'], n_win, H, C, K, bw['dil'], hat, bw['bnd'], 0.25)

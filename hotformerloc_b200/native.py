@@ -102,7 +102,9 @@ SIGNATURES = {
     'hfl_proj_mlp_fused': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     'hfl_window_attn': (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
     'hfl_qkv_attn_supported': (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
-    'hfl_qkv_attn': (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p]),
+    'hfl_qkv_attn': (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _p, _p]),
+    'hfl_qkv_attn_codes_bytes': (C.c_int64, [_i64, _i32, _i32]),
+    'hfl_qkv_attn_codes': (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     'hfl_varlen_attn': (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p]),
     'hfl_stem_conv': (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     'hfl_cpe_ln': (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _p]),

@@ -70,10 +70,18 @@ def qkv_attn_supported(H, C, K, dil, hat, bnd) -> bool:
     return bool(N.lib().hfl_qkv_attn_supported(H, C, K, dil, int(hat), bnd))
 
 
-def qkv_attn(y, Wg, bias_g, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale):
+def qkv_attn_codes(xyzb, n_win, K, dil, hat, bnd, use_rpe=True):
+    """Pair codes of a level for qkv_attn (block-invariant; hfl_qkv_attn_codes)."""
+    nb = int(N.lib().hfl_qkv_attn_codes_bytes(n_win, K, int(hat)))
+    codes = torch.empty(max(nb // 4, 1), dtype=torch.int32, device=xyzb.device)
+    N.check(N.lib().hfl_qkv_attn_codes(_p(xyzb), n_win, K, dil, int(hat), bnd, int(use_rpe), _p(codes), _s()))
+    return codes
+
+
+def qkv_attn(y, Wg, bias_g, out, xyzb, rpe, n_win, H, C, K, dil, hat, bnd, scale, codes=None):
     """out = window attention of (y Wqkv^T + b), qkv never materialised (hfl_qkv_attn)."""
     N.check(N.lib().hfl_qkv_attn(_p(y), _p(Wg), _p(bias_g), _p(out), _p(xyzb), _p(rpe), n_win, y.shape[0],
-                                 H, C, K, dil, int(hat), bnd, float(scale), _s()))
+                                 H, C, K, dil, int(hat), bnd, float(scale), _p(codes), _s()))
 
 
 def varlen_attn(qkv, out, cu, ids, B, max_len, H, C, scale):

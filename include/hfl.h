@@ -154,8 +154,16 @@ int hfl_window_attn(const void* qkv, void* out, const int16_t* xyzb, const float
  * hfl_gather_gemm + hfl_window_attn. */
 int hfl_qkv_attn_supported(int32_t H, int32_t C, int32_t K, int32_t dil, int32_t hat, int32_t bnd);
 int hfl_qkv_attn(const void* y, const void* Wg, const float* bias_g, void* out, const int16_t* xyzb,
-                 const float* rpe, int64_t n_win, int64_t rows, int32_t H, int32_t C, int32_t K,
-                 int32_t dil, int32_t hat, int32_t bnd, float scale, void* stream);
+                 const float* rpe, int64_t n_win, int64_t rows, int32_t H, int32_t C, int32_t K, int32_t dil,
+                 int32_t hat, int32_t bnd, float scale, const uint32_t* codes, void* stream);
+/* Optional: the (query, key) pair codes of a level (clamped relative-position table offsets + the same-submap /
+ * relay-token cases; models/layers/octformer_layers.py:144-163, models/octree.py:186-209).  They depend on the
+ * token positions only, not on the block, so a caller running several blocks on one level makes them once
+ * (hfl_qkv_attn_codes_bytes() bytes) and passes them to every hfl_qkv_attn of that level (with the same K, dil, hat,
+ * bnd and rpe != NULL); with codes == NULL the kernel derives them per tile. */
+int64_t hfl_qkv_attn_codes_bytes(int64_t n_win, int32_t K, int32_t hat);
+int hfl_qkv_attn_codes(const int16_t* xyzb, int64_t n_win, int32_t K, int32_t dil, int32_t hat, int32_t bnd,
+                       int32_t use_rpe, uint32_t* codes, void* stream);
 
 /* Relay-token self-attention over ragged per-submap sequences
  * (hotformerloc_backbone.py:83-119 with the mask of models/octree.py:229-265). */

@@ -235,6 +235,11 @@ def test_qkv_attn_fused(K, dil, hat, H, n_groups):
     ref = _ref_window_attn(qkv, tok, rpe, K, dil, hat, H, bnd)
     err = (out.float().cpu() - ref).abs().max().item()
     assert err < 3e-2, err
+    # pair codes made once per level (hfl_qkv_attn_codes) instead of per tile: bit-identical output
+    codes = _ops().qkv_attn_codes(tok.to(DEV), n_win, K, dil, hat, bnd, True)
+    out2 = torch.zeros_like(out)
+    _ops().qkv_attn(y, Wg, bg, out2, tok.to(DEV), rpe, n_win, H, C, K, dil, hat, bnd, 0.25, codes=codes)
+    assert torch.equal(out2, out)
     # no RPE (disable_RPE)
     out.zero_()
     _ops().qkv_attn(y, Wg, bg, out, tok.to(DEV), None, n_win, H, C, K, dil, hat, bnd, 0.25)

@@ -17,12 +17,14 @@ bnd = 38
 rpe = torch.randn(3 * (2 * bnd + 1), H, device=DEV) * 0.5
 Wg, bg = ops.regroup_qkv(W, b)
 out = torch.zeros(rows, C, device=DEV, dtype=torch.bfloat16)
+import os
+CODES = ops.qkv_attn_codes(tok, n_win, K, 1, hat, bnd, True) if os.environ.get('QA_CODES', '1') == '1' else None
 for _ in range(3):
-    ops.qkv_attn(y, Wg, bg, out, tok, rpe, n_win, H, C, K, 1, hat, bnd, 0.25)
+    ops.qkv_attn(y, Wg, bg, out, tok, rpe, n_win, H, C, K, 1, hat, bnd, 0.25, codes=CODES)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(5):
-    ops.qkv_attn(y, Wg, bg, out, tok, rpe, n_win, H, C, K, 1, hat, bnd, 0.25)
+    ops.qkv_attn(y, Wg, bg, out, tok, rpe, n_win, H, C, K, 1, hat, bnd, 0.25, codes=CODES)
 e.record(); torch.cuda.synchronize()
 print('qkv_attn n_win=%d: %.3f ms' % (n_win, s.elapsed_time(e) / 5))
