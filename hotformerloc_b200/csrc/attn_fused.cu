@@ -29,9 +29,10 @@
 //   4. O drain    TMEM -> 1/rowsum -> bf16 -> global (32 B per row and head)
 // Warp roles (320 threads, 168 registers, 1 CTA / SM, persistent over tiles):
 //   0-7  softmax / drain: team = warp / 4 = window slot of the tile, lane quadrant = warp % 4; per head group
-//        the team drains half of the QKV chunk and runs its two units one after the other (the PV product
-//        of the first overlaps the softmax of the second); the two teams are not synchronised with each other
-//        inside a group
+//        the team runs its two units TOGETHER (one bias look-up serves both heads of the thread), and while their
+//        PV products run it stages the next group: Q / K as soon as every S product has completed, V^T once the
+//        PV products have; the two teams only meet at the MMA barriers.  The (query, key) pair codes come from
+//        k_pair_codes (made once per level, block-invariant) or are derived per tile when the caller passes none
 //   8    tcgen05.mma issue + TMEM alloc          9   TMA producer (lanes 0-1 weights, lane 2 y tiles)
 // Tensor memory (512 columns): QKV chunk 0-191 | four unit buffers of 64 columns at 192 + 64 (2 window + hp).
 #include <cuda.h>
