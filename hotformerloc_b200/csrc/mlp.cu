@@ -44,6 +44,7 @@ struct MlpParams {
   const float* ln_g;          // [C] norm2
   const float* ln_b;
   float ln_eps;
+  int mc;                     // PJ, C = 256: clusters of two CTAs share every weight load (TMA multicast)
 };
 
 // GELU (erf form) of two values at once, given h = x / 2 (the epilogue folds the halving into
@@ -285,8 +286,19 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + ML_BM - 1) / ML_BM;
-  const int n_my = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
-  const int rot = blockIdx.x % NCH;   // every CTA walks the hidden chunks in its own rotation (spreads the L2 reads)
+  // Weight multicast (mc): the two CTAs of a cluster stream the SAME weights in the same order -- every slot is
+  // filled by two half-size loads, one issued by each CTA and delivered to both (half the L2 reads and half the
+  // TMA issue work per SM; the chunk phase demands ~60 B/clock of weights per SM, about what L2 gives 148
+  // independent streams).  Both run the same number of tiles (a dummy tile beyond M stores nothing).
+  const bool mc = PJ && p.mc != 0;
+  const uint32_t crank = mc ? ptx::cluster_ctarank() : 0u;
+  int n_my = (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  if (mc) {
+    const int n_peer = (m_tiles - (int)(blockIdx.x ^ 1u) + (int)gridDim.x - 1) / (int)gridDim.x;
+    n_my = n_my > n_peer ? n_my : n_peer;
+  }
+  // every CTA (pair) walks the hidden chunks in its own rotation (spreads the L2 reads)
+  const int rot = (mc ? (blockIdx.x >> 1) : blockIdx.x) % NCH;
   long long lacc[23];                 // per-thread cycle counters (registers; dead code unless profiling)
 #pragma unroll
   for (int i = 0; i < 23; ++i) lacc[i] = 0;
@@ -300,7 +312,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
     }
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, 1); }
+    for (int s = 0; s < RING; ++s) { ptx::mbar_init(w_full + 8 * s, 1); ptx::mbar_init(w_empty + 8 * s, mc ? 2 : 1); }
     for (int k = 0; k < 4; ++k) ptx::mbar_init(a1_full + 8 * k, PJ ? 4 : 128);   // PJ: the 4 epilogue warps of the K block's column half
     ptx::mbar_init(o_full, 1);
     ptx::mbar_init(c0_full, 1);
@@ -315,6 +327,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (mc) ptx::cluster_sync();                               // the peer's barriers exist before anything is sent to them
   const uint32_t tmem_base = *tmem_ptr_s;
   const uint32_t t_acc2 = tmem_base + 256;
 
@@ -327,30 +340,39 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
       ptx::prefetch_tmap(&tm_w2);
       uint32_t g = 0;
       // every load is one 32 KB box (64 K-columns, rows, K blocks): {64, 128, 2} or {64, 256, 1}
-      auto load = [&](const CUtensorMap* tm, int row0, int kblk) {
+      // mc: the tensor maps carry HALF boxes ({64, 128, 1}); by_rows = the slot's halves are row halves of one K
+      // block (W2, Wp), else the two K blocks of the slot (W1)
+      auto load = [&](const CUtensorMap* tm, int row0, int kblk, bool by_rows) {
         if ((int)(g % (uint32_t)ML_ISSUERS) == lane) {
           const uint32_t s = g % RING, ph = (g / RING) & 1;
+          // mc: w_empty collects the MMA completion of BOTH CTAs (multicast commit): the slot is free in the pair
           { ML_T0(); ptx::mbar_wait_sleep(w_empty + 8 * s, ph ^ 1, 64); ML_ACC(13); }
-          ptx::mbar_arrive_expect_tx(w_full + 8 * s, ML_SLOT);
-          ptx::tma_load_3d(sW + s * ML_SLOT, tm, w_full + 8 * s, 0, row0, kblk);
+          if (mc) {
+            ptx::mbar_arrive_expect_tx(w_full + 8 * s, ML_SLOT);
+            ptx::tma_load_3d_mc(sW + s * ML_SLOT + crank * (ML_SLOT / 2), tm, w_full + 8 * s, 0,
+                                by_rows ? row0 + (int)crank * 128 : row0, by_rows ? kblk : kblk + (int)crank, 0x3);
+          } else {
+            ptx::mbar_arrive_expect_tx(w_full + 8 * s, ML_SLOT);
+            ptx::tma_load_3d(sW + s * ML_SLOT, tm, w_full + 8 * s, 0, row0, kblk);
+          }
         }
         ++g;
       };
       auto load_w1 = [&](int j) {
         const int jr = (j + rot) % NCH;
-        for (int h = 0; h < G1S; ++h) load(&tm_w1, jr * ML_CH, 2 * h);
+        for (int h = 0; h < G1S; ++h) load(&tm_w1, jr * ML_CH, 2 * h, false);
       };
       auto load_w2 = [&](int j) {
         const int jr = (j + rot) % NCH;
-        if (C == 256) { load(&tm_w2, 0, 2 * jr); load(&tm_w2, 0, 2 * jr + 1); }
-        else load(&tm_w2, 0, 2 * jr);
+        if (C == 256) { load(&tm_w2, 0, 2 * jr, true); load(&tm_w2, 0, 2 * jr + 1, true); }
+        else load(&tm_w2, 0, 2 * jr, true);
       };
       // same order as the MMA issuer: G1(0) G1(1) | G2(j) G1(j+2) ... (G1 runs into the next tile)
       for (int it = 0; it < n_my; ++it) {
         if constexpr (PJ) {
           // Wp (K-major [C, C]): C = 256 -> four {64, 256, 1} boxes, C = 128 -> one {64, 128, 2} box
-          if (C == 256) { for (int kb = 0; kb < 4; ++kb) load(&tm_wp, 0, kb); }
-          else load(&tm_wp, 0, 0);
+          if (C == 256) { for (int kb = 0; kb < 4; ++kb) load(&tm_wp, 0, kb, true); }
+          else load(&tm_wp, 0, 0, true);
           load_w1(0); load_w1(1);
           for (int j = 0; j < NCH; ++j) {
             load_w2(j);
@@ -451,7 +473,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
             for (int k = 0; k < 4; ++k)
               ptx::umma_bf16(tmem_base + b * ML_CH, ad + 2 * k, bd + 2 * k, idesc1, (h | kk | k) != 0);
           }
-          ptx::umma_commit(w_empty + 8 * s);
+          if (mc) ptx::umma_commit_mc(w_empty + 8 * s, 0x3); else ptx::umma_commit(w_empty + 8 * s);
           ML_ACC(5);
         }
         ptx::umma_commit(c1_full + 8 * b);
@@ -477,7 +499,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16_ts(t_acc2, ta + 8 * k, bd + 2 * k, idesc2, PJ || (j | kb | k) != 0);   // PJ: acc2 was seeded by epilogue 0
-          if (C == 256 || kb == 1) { ptx::umma_commit(w_empty + 8 * s); ++g; }
+          if (C == 256 || kb == 1) { if (mc) ptx::umma_commit_mc(w_empty + 8 * s, 0x3); else ptx::umma_commit(w_empty + 8 * s); ++g; }
           ML_ACC(6);
         }
         if (j == NCH - 1) ptx::umma_commit(c2_full);
@@ -502,7 +524,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
             for (int k = 0; k < 4; ++k)
               ptx::umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc0, (kb | k) != 0);
           }
-          ptx::umma_commit(w_empty + 8 * s);
+          if (mc) ptx::umma_commit_mc(w_empty + 8 * s, 0x3); else ptx::umma_commit(w_empty + 8 * s);
         }
         ptx::umma_commit(c0_full);
       };
@@ -814,6 +836,7 @@ k_mlp_fused(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ C
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (mc) ptx::cluster_sync();                               // nothing of the peer is in flight towards this CTA any more
   if (warp == 8) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -844,7 +867,21 @@ static int launch_mlp(const CUtensorMap& t1, const CUtensorMap& t2, const CUtens
                                 MlpSmem<C, PJ>::TOTAL));
   const int m_tiles = (p.M + ML_BM - 1) / ML_BM;
   const int sms = sm_count();
-  const int grid = m_tiles < sms ? m_tiles : sms;
+  int grid = m_tiles < sms ? m_tiles : sms;
+  if (p.mc) {
+    // clusters of two CTAs (weight multicast): an even grid, launched with the cluster attribute
+    grid = (grid + 1) & ~1;
+    if (grid > (sms & ~1)) grid = sms & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(ML_THREADS); cfg.dynamicSmemBytes = MlpSmem<C, PJ>::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    HFL_CUDA(cudaLaunchKernelEx(&cfg, k_mlp_fused<C, PROF, PJ>, t1, t2, to, tp, p));
+    ::hfl::g_launches.fetch_add(1, std::memory_order_relaxed);
+    return HFL_OK;
+  }
   HFL_LAUNCH((k_mlp_fused<C, PROF, PJ><<<grid, ML_THREADS, MlpSmem<C, PJ>::TOTAL, st>>>(t1, t2, to, tp, p)));
   return HFL_OK;
 }
@@ -866,13 +903,16 @@ static int mlp_dispatch(const void* A, const void* Wp, const float* bp, const fl
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUresult cr = make_map(&t1, W1, 4 * C, C, 128, 2);
+  // weight multicast between the two CTAs of a cluster (block kernel, C = 256): half boxes, see the kernel
+  static const bool env_mc = !(getenv("HFL_MLP_MULTICAST") && getenv("HFL_MLP_MULTICAST")[0] == '0');
+  const bool mc = pj && C == 256 && env_mc && M >= 2 * ML_BM;
+  CUresult cr = mc ? make_map(&t1, W1, 4 * C, C, 128, 1) : make_map(&t1, W1, 4 * C, C, 128, 2);
   if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W1) failed%s (%lld)", "", (long long)cr);
-  cr = C == 256 ? make_map(&t2, W2, C, 4 * C, 256, 1) : make_map(&t2, W2, C, 4 * C, 128, 2);
+  cr = mc ? make_map(&t2, W2, C, 4 * C, 128, 1) : C == 256 ? make_map(&t2, W2, C, 4 * C, 256, 1) : make_map(&t2, W2, C, 4 * C, 128, 2);
   if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (W2) failed%s (%lld)", "", (long long)cr);
   to = t1; tp = t1;
   if (pj) {
-    cr = C == 256 ? make_map(&tp, Wp, C, C, 256, 1) : make_map(&tp, Wp, C, C, 128, 2);
+    cr = mc ? make_map(&tp, Wp, C, C, 128, 1) : C == 256 ? make_map(&tp, Wp, C, C, 256, 1) : make_map(&tp, Wp, C, C, 128, 2);
     if (cr != CUDA_SUCCESS) return fail(HFL_ERR_CUDA, "tensor map (Wp) failed%s (%lld)", "", (long long)cr);
     // o tile: 128 x 64 boxes of the row-major [M, C] matrix, rows >= M zero-filled
     cuuint64_t adims[2] = {(cuuint64_t)C, (cuuint64_t)M};
@@ -889,7 +929,7 @@ static int mlp_dispatch(const void* A, const void* Wp, const float* bp, const fl
   if (want_prof && !prof) cudaMalloc(&prof, 32 * sizeof(long long));
   if (want_prof) cudaMemsetAsync(prof, 0, 32 * sizeof(long long), st);
   MlpParams p{(const __nv_bfloat16*)A, (int)M, b1, b2, res, out_f32, (__nv_bfloat16*)out_bf16, out_rows,
-              dbg, want_prof ? prof : nullptr, bp, ln_g, ln_b, 1e-5f};
+              dbg, want_prof ? prof : nullptr, bp, ln_g, ln_b, 1e-5f, mc ? 1 : 0};
   int rc;
   if (pj && want_prof && C == 256) rc = launch_mlp<256, true, true>(t1, t2, to, tp, p, st);
   else if (pj) rc = C == 128 ? launch_mlp<128, false, true>(t1, t2, to, tp, p, st) : launch_mlp<256, false, true>(t1, t2, to, tp, p, st);
