@@ -328,17 +328,32 @@ k_qkv_attn(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUt
           else if (ptx::mbar_try_wait(y_full, (it + 1) & 1)) { ptx::tc_fence_after(); issue_qkv(0); }
           else deferred = true;
         }
+        // PV products in the order the TEAMS deliver P (a team delivers both of its units together): whichever
+        // window's softmax finishes first gets its products first, the other team is not made to wait behind it
+        {
+          QA_T0();
+          uint32_t pend = 3u, spins = 0;
+          while (pend) {
 #pragma unroll
-        for (int tt = 0; tt < 4; ++tt) {
-          const int t = (tt & 1) * 2 + (tt >> 1);          // the order the teams finish them: 0, 2, 1, 3
-          { QA_T0(); ptx::mbar_wait(p_ready + 8 * t, ph); QA_ACC(3); }
-          ptx::tc_fence_after();
-          const uint64_t vd = ptx::umma_desc_sw128(sV + t * 4096);
+            for (int w2 = 0; w2 < 2; ++w2) {
+              if (!((pend >> w2) & 1u)) continue;
+              if (!ptx::mbar_try_wait(p_ready + 8 * (2 * w2), ph) || !ptx::mbar_try_wait(p_ready + 8 * (2 * w2 + 1), ph)) continue;
+              ptx::tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < NCH; ++kk)
-            ptx::umma_bf16_ts(tmem_base + T_U + t * 64 + 32, tmem_base + T_U + t * 64 + 8 * kk, vd + 2 * kk,
-                              idesc_pv, kk != 0);
-          ptx::umma_commit(o_full + 8 * t);
+              for (int hp = 0; hp < 2; ++hp) {
+                const int t = 2 * w2 + hp;
+                const uint64_t vd = ptx::umma_desc_sw128(sV + t * 4096);
+#pragma unroll
+                for (int kk = 0; kk < NCH; ++kk)
+                  ptx::umma_bf16_ts(tmem_base + T_U + t * 64 + 32, tmem_base + T_U + t * 64 + 8 * kk, vd + 2 * kk,
+                                    idesc_pv, kk != 0);
+                ptx::umma_commit(o_full + 8 * t);
+              }
+              pend &= ~(1u << w2);
+            }
+            if (++spins > (1u << 26)) __trap();
+          }
+          QA_ACC(3);
         }
         ptx::umma_commit(attn_done);
         if (deferred) {
